@@ -1,0 +1,106 @@
+"""ctypes binding of libgraphecho_b200.so (the C-ABI in include/graphecho_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing, or a tensor is not
+a CUDA tensor, the call raises.  Only raw device pointers, sizes and the current CUDA
+stream cross this boundary.
+"""
+from __future__ import annotations
+
+import ctypes
+import re
+from ctypes import c_int, c_size_t, c_void_p, c_char_p, c_ulonglong, c_float, c_double, c_longlong
+from pathlib import Path
+
+import torch
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libgraphecho_b200.so"
+HEADER = PKG.parent / "include" / "graphecho_b200.h"
+
+P, I, Z, F, L = c_void_p, c_int, c_size_t, c_float, c_longlong
+
+# name -> (restype, argtypes)
+_SIGNATURES = {
+    "ge_version": (c_int, []),
+    "ge_last_error": (c_char_p, []),
+    "ge_device_sm_count": (c_int, []),
+    "ge_launch_count": (c_ulonglong, []),
+    "ge_affinity_pairwise_fwd": (c_int, [P, P, P, P, P, I, I, I, I, P]),
+    "ge_affinity_pairwise_bwd_workspace_bytes": (c_size_t, [I, I, I, I]),
+    "ge_affinity_pairwise_bwd": (c_int, [P, P, P, P, P, P, P, P, P, Z, I, I, I, I, P]),
+    "ge_sinkhorn_rpm_cluster_size": (c_int, [I, I, I]),
+    "ge_sinkhorn_rpm_fwd": (c_int, [P, P, P, P, P, I, I, I, I, I, I, P]),
+    "ge_sinkhorn_rpm_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, P]),
+    "ge_sinkhorn_distance_fwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, c_double, P]),
+    "ge_sinkhorn_distance_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
+    "ge_knn_graph_workspace_bytes": (c_size_t, [I, I, I, I]),
+    "ge_knn_graph": (c_int, [P, P, P, P, P, Z, I, I, I, I, I, I, P]),
+    "ge_mrconv_gather_fwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P]),
+    "ge_mrconv_gather_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P]),
+    "ge_tgcn_pool_concat_fwd": (c_int, [P, L, P, I, L, I, I, I, I, I, I, P]),
+    "ge_tgcn_pool_concat_bwd": (c_int, [P, P, I, L, I, I, I, I, I, I, P]),
+    "ge_upsample_add_fwd": (c_int, [P, P, P, I, I, I, I, I, I, I, P]),
+    "ge_upsample_bwd": (c_int, [P, P, I, I, I, I, I, I, I, P]),
+    "ge_chan_stats": (c_int, [P, P, P, I, I, I, I, F, P]),
+    "ge_gn_relu_upsample_fwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "ge_gn_relu_upsample_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "ge_seg_tail_fwd": (c_int, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "ge_seg_tail_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P]),
+}
+
+_lib = None
+
+
+class GraphEchoNativeError(RuntimeError):
+    pass
+
+
+def header_symbols() -> list[str]:
+    """Every function the public header declares (used by the ABI export test)."""
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ge_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise GraphEchoNativeError(
+                f"{LIB_PATH} is missing: build it with `python -m graphecho_b200.build` "
+                "(graphecho_b200 has no CPU or PyTorch-eager fallback)")
+        handle = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().ge_last_error().decode("utf-8", "replace")
+
+
+def ptr(t: torch.Tensor | None) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise GraphEchoNativeError("graphecho_b200 kernels take CUDA tensors only (no CPU fallback)")
+    return c_void_p(t.data_ptr())
+
+
+def stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point and raise on a non-zero status."""
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        kind = "argument/shape" if rc < 0 else "CUDA"
+        raise GraphEchoNativeError(f"{name} failed ({kind} error {rc}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(lib().ge_launch_count())

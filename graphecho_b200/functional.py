@@ -1,0 +1,412 @@
+"""torch.autograd.Function shells around the C-ABI kernels (libgraphecho_b200.so).
+
+Every function here takes CUDA tensors only; there is no eager/CPU fallback.  The modules in
+graphecho_b200.models / graphecho_b200.utils compose these with library GEMMs/convs.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _cabi
+from ._cabi import call, ptr, stream
+from ctypes import c_int, c_float, c_double, c_size_t, c_longlong
+
+F32, BF16 = 0, 1
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise _cabi.GraphEchoNativeError(f"unsupported activation dtype {t.dtype} (fp32 or bf16)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous (no copy when already so)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _cabi.GraphEchoNativeError("graphecho_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+# ------------------------------------------------------------------------------------------ K3
+class _AffinityPairwise(Function):
+    @staticmethod
+    def forward(ctx, A, B, w2, b2):
+        _need_cuda(A, B, w2, b2)
+        squeeze = A.dim() == 2
+        A3 = _f32c(A if not squeeze else A.unsqueeze(0))
+        B3 = _f32c(B if not squeeze else B.unsqueeze(0))
+        w2c, b2c = _f32c(w2).view(-1), _f32c(b2).view(-1)
+        batch, N1, H = A3.shape
+        N2 = B3.shape[1]
+        M = torch.empty((batch, N1, N2), device=A.device, dtype=torch.float32)
+        call("ge_affinity_pairwise_fwd", ptr(A3), ptr(B3), ptr(w2c), ptr(b2c), ptr(M),
+             batch, N1, N2, H, stream())
+        ctx.save_for_backward(A3, B3, w2c)
+        ctx.squeeze = squeeze
+        ctx.shapes = (w2.shape, b2.shape)
+        return M[0] if squeeze else M
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dM):
+        A3, B3, w2c = ctx.saved_tensors
+        batch, N1, H = A3.shape
+        N2 = B3.shape[1]
+        dM3 = _f32c(dM if not ctx.squeeze else dM.unsqueeze(0))
+        dA, dB = torch.empty_like(A3), torch.empty_like(B3)
+        dw2 = torch.empty_like(w2c)
+        db2 = torch.empty(1, device=A3.device, dtype=torch.float32)
+        nbytes = _cabi.lib().ge_affinity_pairwise_bwd_workspace_bytes(batch, N1, N2, H)
+        ws = torch.empty(max(nbytes, 4), device=A3.device, dtype=torch.uint8)
+        call("ge_affinity_pairwise_bwd", ptr(A3), ptr(B3), ptr(w2c), ptr(dM3), ptr(dA), ptr(dB),
+             ptr(dw2), ptr(db2), ptr(ws), c_size_t(ws.numel()), batch, N1, N2, H, stream())
+        if ctx.squeeze:
+            dA, dB = dA[0], dB[0]
+        return dA, dB, dw2.view(ctx.shapes[0]), db2.view(ctx.shapes[1])
+
+
+def affinity_pairwise(A, B, w2, b2):
+    """M[i,j] = sum_k w2[k] relu(A[i,k] + B[j,k]) + b2.   A [N1,H] / [b,N1,H], B likewise."""
+    return _AffinityPairwise.apply(A, B, w2, b2)
+
+
+# ------------------------------------------------------------------------------------------ K4
+class _SinkhornRpm(Function):
+    @staticmethod
+    def forward(ctx, M, n_iters, instnorm, cluster_size):
+        _need_cuda(M)
+        squeeze = M.dim() == 2
+        M3 = _f32c(M if not squeeze else M.unsqueeze(0))
+        batch, N1, N2 = M3.shape
+        dev = M.device
+        P = torch.empty_like(M3)
+        hist_r = torch.empty((batch, max(n_iters, 1), N1), device=dev, dtype=torch.float32)
+        hist_c = torch.empty((batch, max(n_iters, 1), N2), device=dev, dtype=torch.float32)
+        stats = torch.empty((batch, 4), device=dev, dtype=torch.float32)
+        call("ge_sinkhorn_rpm_fwd", ptr(M3), ptr(P), ptr(hist_r), ptr(hist_c), ptr(stats),
+             batch, N1, N2, int(n_iters), int(bool(instnorm)), int(cluster_size), stream())
+        ctx.save_for_backward(M3, hist_r, hist_c, stats)
+        ctx.cfg = (int(n_iters), int(bool(instnorm)), int(cluster_size), squeeze)
+        return P[0] if squeeze else P
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        M3, hist_r, hist_c, stats = ctx.saved_tensors
+        n_iters, instnorm, cluster_size, squeeze = ctx.cfg
+        batch, N1, N2 = M3.shape
+        G3 = _f32c(G if not squeeze else G.unsqueeze(0))
+        dM = torch.empty_like(M3)
+        call("ge_sinkhorn_rpm_bwd", ptr(M3), ptr(G3), ptr(hist_r), ptr(hist_c), ptr(stats), ptr(dM),
+             batch, N1, N2, n_iters, instnorm, cluster_size, stream())
+        return (dM[0] if squeeze else dM), None, None, None
+
+
+def sinkhorn_rpm_exp(M, n_iters=20, instnorm=True, cluster_size=0):
+    """exp(sinkhorn_rpm(InstanceNorm(M), n_iters, slack=True)) for M [N1,N2] or [b,N1,N2]."""
+    return _SinkhornRpm.apply(M, n_iters, instnorm, cluster_size)
+
+
+# ------------------------------------------------------------------------------------------ K5
+class _SinkhornDistance(Function):
+    @staticmethod
+    def forward(ctx, x, y, eps, max_iter, thresh):
+        _need_cuda(x, y)
+        x3, y3 = _f32c(x), _f32c(y)
+        B, P1, D = x3.shape
+        P2 = y3.shape[1]
+        dev = x.device
+        C = torch.empty((B, P1, P2), device=dev, dtype=torch.float32)
+        pi = torch.empty_like(C)
+        cost = torch.empty(B, device=dev, dtype=torch.float32)
+        mi = max(int(max_iter), 1)
+        hist_u = torch.empty((B, mi, P1), device=dev, dtype=torch.float32)
+        hist_v = torch.empty((B, mi, P2), device=dev, dtype=torch.float32)
+        err = torch.empty((B, mi), device=dev, dtype=torch.float32)
+        nits = torch.zeros(1, device=dev, dtype=torch.int32)
+        call("ge_sinkhorn_distance_fwd", ptr(x3), ptr(y3), ptr(C), ptr(pi), ptr(cost), ptr(hist_u),
+             ptr(hist_v), ptr(err), ptr(nits), B, P1, P2, D, c_float(eps), int(max_iter),
+             c_double(thresh), stream())
+        ctx.save_for_backward(x3, y3, C, hist_u, hist_v, nits)
+        ctx.cfg = (float(eps), int(max_iter))
+        ctx.mark_non_differentiable(pi, C, nits)
+        return cost, pi, C, nits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gcost, gpi, gC, gn):
+        x3, y3, C, hist_u, hist_v, nits = ctx.saved_tensors
+        eps, max_iter = ctx.cfg
+        B, P1, D = x3.shape
+        P2 = y3.shape[1]
+        g = _f32c(gcost)
+        dC = torch.empty_like(C)
+        dx, dy = torch.empty_like(x3), torch.empty_like(y3)
+        call("ge_sinkhorn_distance_bwd", ptr(x3), ptr(y3), ptr(C), ptr(hist_u), ptr(hist_v), ptr(nits),
+             ptr(g), ptr(dC), ptr(dx), ptr(dy), B, P1, P2, D, c_float(eps), max_iter, stream())
+        return dx, dy, None, None, None
+
+
+def sinkhorn_distance(x, y, eps, max_iter, thresh=0.1):
+    """x [B,P1,D], y [B,P2,D] -> (cost [B], pi, C, nits).  Gradients flow through `cost`."""
+    return _SinkhornDistance.apply(x, y, eps, max_iter, thresh)
+
+
+# ------------------------------------------------------------------------------------------ K1
+@torch.no_grad()
+def knn_graph(x, y=None, k=9, dilation=1, relative_pos=None):
+    """x [B,C,N(,1)], y [B,C,M(,1)] or None -> int64 edge_index [2,B,N,k] (vig.py:369-381)."""
+    _need_cuda(x, y, relative_pos)
+    B, C = x.shape[0], x.shape[1]
+    x3 = _f32c(x.reshape(B, C, -1))
+    N = x3.shape[2]
+    y3 = None
+    M = N
+    if y is not None:
+        y3 = _f32c(y.reshape(B, C, -1))
+        M = y3.shape[2]
+    rel = None
+    if relative_pos is not None:
+        rel = _f32c(relative_pos.reshape(-1, relative_pos.shape[-2], relative_pos.shape[-1]))
+        if rel.shape[0] != 1 or rel.shape[1] != N or rel.shape[2] != M:
+            raise _cabi.GraphEchoNativeError(f"relative_pos must be [1,{N},{M}], got {tuple(relative_pos.shape)}")
+    out = torch.empty((2, B, N, k), device=x.device, dtype=torch.int64)
+    nbytes = _cabi.lib().ge_knn_graph_workspace_bytes(B, C, N, M)
+    ws = torch.empty(max(nbytes, 4), device=x.device, dtype=torch.uint8)
+    call("ge_knn_graph", ptr(x3), ptr(y3), ptr(rel), ptr(out), ptr(ws), c_size_t(ws.numel()),
+         B, C, N, M, int(k), int(dilation), stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K2
+class _MRGather(Function):
+    @staticmethod
+    def forward(ctx, x, y, idx_nbr, idx_ctr):
+        _need_cuda(x, y, idx_nbr, idx_ctr)
+        B, C = x.shape[0], x.shape[1]
+        x3 = _f32c(x.reshape(B, C, -1))
+        N = x3.shape[2]
+        y3, M = None, N
+        if y is not None:
+            y3 = _f32c(y.reshape(B, C, -1))
+            M = y3.shape[2]
+        i0 = idx_nbr.contiguous()
+        i1 = idx_ctr.contiguous() if idx_ctr is not None else None
+        k = i0.shape[-1]
+        out = torch.empty((B, 2 * C, N), device=x.device, dtype=torch.float32)
+        argk = torch.empty((B, C, N), device=x.device, dtype=torch.uint8)
+        call("ge_mrconv_gather_fwd", ptr(x3), ptr(y3), ptr(i0), ptr(i1), ptr(out), ptr(argk),
+             B, C, N, M, k, stream())
+        ctx.save_for_backward(i0, i1 if i1 is not None else i0, argk)
+        ctx.cfg = (B, C, N, M, k, i1 is not None, y is not None, x.shape, None if y is None else y.shape)
+        ctx.mark_non_differentiable(argk)
+        return out, argk
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout, _):
+        i0, i1, argk = ctx.saved_tensors
+        B, C, N, M, k, has_ctr, has_y, xshape, yshape = ctx.cfg
+        d = _f32c(dout)
+        dx = torch.empty((B, C, N), device=d.device, dtype=torch.float32)
+        dy = torch.zeros((B, C, M), device=d.device, dtype=torch.float32) if has_y else None
+        call("ge_mrconv_gather_bwd", ptr(d), ptr(i0), ptr(i1 if has_ctr else None), ptr(argk), ptr(dx), ptr(dy),
+             B, C, N, M, k, stream())
+        return dx.view(xshape), (dy.view(yshape) if has_y else None), None, None
+
+
+def mr_gather(x, edge_index, y=None, identity_centre=True):
+    """Channel-interleaved [x ; max_k(y_j - x_i)]  ->  [B, 2C, N, 1]  (vig.py:96-104)."""
+    idx_nbr = edge_index[0]
+    idx_ctr = None if identity_centre else edge_index[1]
+    out, _ = _MRGather.apply(x, y, idx_nbr, idx_ctr)
+    return out.unsqueeze(-1)
+
+
+# ------------------------------------------------------------------------------------------ K6
+def _nhwc_view(t: torch.Tensor):
+    """[F,C,H,W] logical tensor -> NHWC-dense tensor sharing storage when already channels_last."""
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+class _PoolConcat(Function):
+    @staticmethod
+    def forward(ctx, rs, *levels):
+        _need_cuda(*levels)
+        lv = [_nhwc_view(t) for t in levels]
+        F_ = lv[0].shape[0]
+        Ctot = sum(t.shape[1] for t in lv)
+        Ho, Wo = lv[0].shape[2] // rs[0], lv[0].shape[3] // rs[0]
+        out = torch.empty((F_, Ctot, Ho, Wo), device=lv[0].device, dtype=torch.float32,
+                          memory_format=torch.channels_last)
+        coff = 0
+        meta = []
+        for t, r in zip(lv, rs):
+            _, C, H, W = t.shape
+            if (H // r, W // r) != (Ho, Wo):
+                raise _cabi.GraphEchoNativeError(
+                    f"pooled sizes differ: level {tuple(t.shape)} with r={r} vs {(Ho, Wo)} (TGCN.py:64-70 would fail in torch.cat)")
+            call("ge_tgcn_pool_concat_fwd", ptr(t), c_longlong(H * W * C), ptr(out), _dtype_code(t),
+                 c_longlong(F_), H, W, C, int(r), Ctot, coff, stream())
+            meta.append((t.shape, t.dtype, int(r), coff))
+            coff += C
+        ctx.meta = meta
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        d = dout.float().contiguous(memory_format=torch.channels_last)
+        F_, Ctot = d.shape[0], d.shape[1]
+        grads = []
+        for shape, dtype, r, coff in ctx.meta:
+            _, C, H, W = shape
+            g = torch.empty(shape, device=d.device, dtype=dtype, memory_format=torch.channels_last)
+            call("ge_tgcn_pool_concat_bwd", ptr(d), ptr(g), _dtype_code(g), c_longlong(F_), H, W, C, r, Ctot, coff, stream())
+            grads.append(g)
+        return (None, *grads)
+
+
+def pool_concat(levels, rs):
+    """avg_pool2d(level_l, r_l) for every level, concatenated on channels -> fp32 channels_last."""
+    return _PoolConcat.apply(tuple(int(r) for r in rs), *levels)
+
+
+# ------------------------------------------------------------------------------------------ K7
+class _UpsampleAdd(Function):
+    @staticmethod
+    def forward(ctx, top, lateral, size):
+        _need_cuda(top, lateral)
+        t = _nhwc_view(top)
+        N, C, h, w = t.shape
+        H, W = size
+        lat = None
+        if lateral is not None:
+            lat = _nhwc_view(lateral.to(t.dtype))
+        out = torch.empty((N, C, H, W), device=t.device, dtype=t.dtype, memory_format=torch.channels_last)
+        call("ge_upsample_add_fwd", ptr(t), ptr(lat), ptr(out), _dtype_code(t), N, h, w, H, W, C, stream())
+        ctx.cfg = (N, C, h, w, H, W, lateral is not None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        N, C, h, w, H, W, has_lat = ctx.cfg
+        d = _nhwc_view(dout)
+        dtop = torch.empty((N, C, h, w), device=d.device, dtype=d.dtype, memory_format=torch.channels_last)
+        call("ge_upsample_bwd", ptr(d), ptr(dtop), _dtype_code(d), N, h, w, H, W, C, stream())
+        return dtop, (d if has_lat else None), None
+
+
+def upsample_add(top, lateral):
+    """bilinear(align_corners=True) up-sampling of `top` to lateral's size, plus lateral."""
+    return _UpsampleAdd.apply(top, lateral, (lateral.shape[2], lateral.shape[3]))
+
+
+def upsample_bilinear(x, size):
+    return _UpsampleAdd.apply(x, None, (int(size[0]), int(size[1])))
+
+
+class _GnReluUpsample(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, size, eps):
+        _need_cuda(x, gamma, beta)
+        xc = _nhwc_view(x)
+        N, C, h, w = xc.shape
+        H, W = size
+        g, b = _f32c(gamma), _f32c(beta)
+        mean = torch.empty((N, C), device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        code = _dtype_code(xc)
+        call("ge_chan_stats", ptr(xc), ptr(mean), ptr(rstd), code, N, h * w, C, c_float(eps), stream())
+        out = torch.empty((N, C, H, W), device=x.device, dtype=xc.dtype, memory_format=torch.channels_last)
+        call("ge_gn_relu_upsample_fwd", ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(out), code,
+             N, h, w, H, W, C, stream())
+        ctx.save_for_backward(xc, mean, rstd, g, b)
+        ctx.cfg = (N, C, h, w, H, W, gamma.dtype, beta.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        xc, mean, rstd, g, b = ctx.saved_tensors
+        N, C, h, w, H, W, gdt, bdt = ctx.cfg
+        d = _nhwc_view(dout.to(xc.dtype))
+        dyh = torch.empty((N, h, w, C), device=d.device, dtype=torch.float32)
+        S1 = torch.empty((N, C), device=d.device, dtype=torch.float32)
+        S2 = torch.empty_like(S1)
+        dx = torch.empty_like(xc)
+        call("ge_gn_relu_upsample_bwd", ptr(d), ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dyh),
+             ptr(S1), ptr(S2), ptr(dx), _dtype_code(xc), N, h, w, H, W, C, stream())
+        return dx, S2.sum(0).to(gdt), S1.sum(0).to(bdt), None, None
+
+
+def gn_relu_upsample(x, gamma, beta, size, eps=1e-5):
+    """_upsample(relu(GroupNorm(C,C)(x)), size) with align_corners=True (fpnseg.py:428-442)."""
+    return _GnReluUpsample.apply(x, gamma, beta, (int(size[0]), int(size[1])), float(eps))
+
+
+class _SegTail(Function):
+    @staticmethod
+    def forward(ctx, s2, s3, s4, s5, W3, b3, scale):
+        _need_cuda(s2, s3, s4, s5, W3, b3)
+        dt = s2.dtype
+        a, b, c, d = (_nhwc_view(t.to(dt)) for t in (s2, s3, s4, s5))
+        N, C, h, w = a.shape
+        nc = W3.shape[0]
+        Wm = _f32c(W3).view(nc, C)
+        bm = _f32c(b3)
+        H, W = h * scale, w * scale
+        q = torch.empty((N, h, w, nc), device=a.device, dtype=torch.float32)
+        logits = torch.empty((N, nc, H, W), device=a.device, dtype=torch.float32)
+        call("ge_seg_tail_fwd", ptr(a), ptr(b), ptr(c), ptr(d), ptr(Wm), ptr(bm), ptr(q), ptr(logits),
+             _dtype_code(a), N, h, w, H, W, C, nc, stream())
+        ctx.save_for_backward(a, b, c, d, Wm)
+        ctx.cfg = (N, C, h, w, H, W, nc, W3.shape, W3.dtype, b3.dtype)
+        return logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dlogits):
+        a, b, c, d, Wm = ctx.saved_tensors
+        N, C, h, w, H, W, nc, wshape, wdt, bdt = ctx.cfg
+        g = _f32c(dlogits)
+        dq = torch.empty((N, h, w, nc), device=g.device, dtype=torch.float32)
+        ds = torch.empty_like(a)
+        dW3 = torch.zeros((nc, C), device=g.device, dtype=torch.float32)
+        db3 = torch.zeros(nc, device=g.device, dtype=torch.float32)
+        call("ge_seg_tail_bwd", ptr(g), ptr(a), ptr(b), ptr(c), ptr(d), ptr(Wm), ptr(dq), ptr(ds), ptr(dW3),
+             ptr(db3), _dtype_code(a), N, h, w, H, W, C, nc, stream())
+        return ds, ds, ds, ds, dW3.view(wshape).to(wdt), db3.to(bdt), None
+
+
+def seg_tail(s2, s3, s4, s5, W3, b3, scale=4):
+    """_upsample(conv3(s2+s3+s4+s5), 4h, 4w) -> fp32 NCHW logits (fpnseg.py:444)."""
+    return _SegTail.apply(s2, s3, s4, s5, W3, b3, int(scale))
+
+
+class _GradReverse(Function):
+    """Gradient reversal (gradient_reversal.py:6-24) without the reference's full clone()."""
+
+    @staticmethod
+    def forward(ctx, x, lambda_):
+        ctx.lambda_ = float(lambda_)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return -ctx.lambda_ * g, None
+
+
+def grad_reverse(x, lambda_):
+    return _GradReverse.apply(x, lambda_)

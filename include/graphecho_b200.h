@@ -1,0 +1,154 @@
+/* graphecho_b200 — C-ABI of the sm_100a kernels behind GraphEcho's data-parallel hot path.
+ *
+ * The reference (xmed-lab/GraphEcho) is pure Python/PyTorch and has no FFI of its own: its
+ * boundary for this path is the nn.Module API (models.fpnseg / models.vig /
+ * models.graph_matching / models.affinity_layer / models.TGCN / utils.sinkhorn_distance).
+ * Each entry point below names the reference op sequence it replaces (file:line under the
+ * reference tree); graphecho_b200/_cabi.py binds them with ctypes and
+ * graphecho_b200/functional.py wraps them in torch.autograd.Function.
+ *
+ * Conventions
+ *  - plain pointers + sizes; every pointer is DEVICE memory owned by the caller
+ *    (inputs, outputs and workspace); the library never allocates, frees or keeps them.
+ *  - tensors are dense in the documented layout; float = fp32.
+ *  - launches are asynchronous on `stream` (a cudaStream_t); no internal sync,
+ *    CUDA-graph capturable.
+ *  - return 0 on success, <0 argument / shape / capacity error, >0 a cudaError_t;
+ *    ge_last_error() gives the text (thread-local).  Nothing falls back to the CPU.
+ */
+#ifndef GRAPHECHO_B200_H
+#define GRAPHECHO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GE_ABI_VERSION 1
+
+typedef void* ge_stream_t; /* cudaStream_t */
+
+/* activation storage types for the NHWC feature-map kernels (math is always fp32) */
+#define GE_DTYPE_F32 0
+#define GE_DTYPE_BF16 1
+
+int ge_version(void);
+const char* ge_last_error(void);
+int ge_device_sm_count(void);
+unsigned long long ge_launch_count(void);
+
+/* ---- K3: pairwise affinity --------------------------------------------------------------
+ * M[b,i,j] = sum_k w2[k]*relu(A[b,i,k] + B[b,j,k]) + b2[0]
+ * Separable form of Affinity.forward (models/affinity_layer.py:52-73): A = fc_M.0 applied to
+ * the project_sr half, B = the project_tg half + bias (dense projections done by the caller).
+ * A [batch,N1,H], B [batch,N2,H], w2 [H], b2 [1], M [batch,N1,N2].  H % 32 == 0, H <= 640. */
+int ge_affinity_pairwise_fwd(const float* A, const float* B, const float* w2, const float* b2,
+                             float* M, int batch, int N1, int N2, int H, ge_stream_t stream);
+size_t ge_affinity_pairwise_bwd_workspace_bytes(int batch, int N1, int N2, int H);
+/* dA [batch,N1,H], dB [batch,N2,H], dw2 [H], db2 [1] (all overwritten). */
+int ge_affinity_pairwise_bwd(const float* A, const float* B, const float* w2, const float* dM,
+                             float* dA, float* dB, float* dw2, float* db2,
+                             void* workspace, size_t workspace_bytes,
+                             int batch, int N1, int N2, int H, ge_stream_t stream);
+
+/* ---- K4: instance-norm + slack Sinkhorn + exp --------------------------------------------
+ * P = exp(sinkhorn_rpm(InstanceNorm2d(1)(M), n_iters, slack=True))
+ * (models/graph_matching.py:574-575 and 637-676).  One thread-block cluster per problem,
+ * matrix resident in (distributed) shared memory for the whole loop.
+ * M, P [batch,N1,N2]; hist_r [batch,n_iters,N1], hist_c [batch,n_iters,N2] receive the row /
+ * column log-potentials after every pass (saved for the backward); stats [batch,4] receives
+ * (mean, rstd, -, -).  apply_instnorm=0 skips the normalisation (plain sinkhorn_rpm).
+ * cluster_size: 0 = choose, else 1/2/4/8/16.  GE_ERR_CAPACITY if N1*N2 does not fit. */
+int ge_sinkhorn_rpm_cluster_size(int N1, int N2, int backward);
+int ge_sinkhorn_rpm_fwd(const float* M, float* P, float* hist_r, float* hist_c, float* stats,
+                        int batch, int N1, int N2, int n_iters, int apply_instnorm,
+                        int cluster_size, ge_stream_t stream);
+/* G = dLoss/dP; dM receives dLoss/dM (exact adjoint of the unrolled iterations). */
+int ge_sinkhorn_rpm_bwd(const float* M, const float* G, const float* hist_r, const float* hist_c,
+                        const float* stats, float* dM, int batch, int N1, int N2, int n_iters,
+                        int apply_instnorm, int cluster_size, ge_stream_t stream);
+
+/* ---- K5: SinkhornDistance ----------------------------------------------------------------
+ * utils/sinkhorn_distance.py:27-86: C_ij = sum_d (x_id-y_jd)^2, <= max_iter log-domain updates
+ * with the batch-mean early stop `err < thresh`, pi = exp((-C+u+v)/eps), cost_b = sum pi*C.
+ * x [B,P1,D], y [B,P2,D]; outputs C, pi [B,P1,P2], cost [B]; saved for backward:
+ * hist_u [B,max_iter,P1], hist_v [B,max_iter,P2], err [B,max_iter], nits [1] (int32, the
+ * number of iterations the reference loop would have executed).  One CTA per batch element;
+ * GE_ERR_CAPACITY if P1*P2 does not fit shared memory. */
+int ge_sinkhorn_distance_fwd(const float* x, const float* y, float* C, float* pi, float* cost,
+                             float* hist_u, float* hist_v, float* err, int* nits,
+                             int B, int P1, int P2, int D, float eps, int max_iter, double thresh,
+                             ge_stream_t stream);
+/* gcost [B] = dLoss/dcost_b; dC [B,P1,P2] scratch/output; dx [B,P1,D], dy [B,P2,D]. */
+int ge_sinkhorn_distance_bwd(const float* x, const float* y, const float* C, const float* hist_u,
+                             const float* hist_v, const int* nits, const float* gcost,
+                             float* dC, float* dx, float* dy,
+                             int B, int P1, int P2, int D, float eps, int max_iter, ge_stream_t stream);
+
+/* ---- K1: dense dilated k-NN graph ----------------------------------------------------------
+ * DenseDilatedKnnGraph.forward (models/vig.py:369-381) incl. F.normalize, (xy_)pairwise_distance
+ * (:232-274), topk (:306/327), centre index + stack (:308-309/328-329) and the dilation stride
+ * (:353).  x [B,C,N], y [B,C,M] or NULL (self graph, M == N), relative_pos [N,M] or NULL,
+ * edge_index int64 [2,B,N,k]; k*dilation <= 64 and <= M.  Ties -> lower key index. */
+size_t ge_knn_graph_workspace_bytes(int B, int C, int N, int M);
+int ge_knn_graph(const float* x, const float* y, const float* relative_pos, long long* edge_index,
+                 void* workspace, size_t workspace_bytes,
+                 int B, int C, int N, int M, int k, int dilation, ge_stream_t stream);
+
+/* ---- K2: max-relative aggregation (gather half of MRConv2d) -------------------------------
+ * models/vig.py:96-104 + batched_index_select (:209-229):
+ * out[b,2c,n] = x[b,c,n]; out[b,2c+1,n] = max_k(y[b,c,idx_nbr[b,n,k]] - x[b,c,idx_ctr[b,n,k]]).
+ * x [B,C,N], y [B,C,M] or NULL (= x), idx_* int64 [B,N,k] (idx_ctr NULL = the point itself),
+ * out [B,2C,N], argk uint8 [B,C,N] (winning neighbour slot, saved for the backward). */
+int ge_mrconv_gather_fwd(const float* x, const float* y, const long long* idx_nbr, const long long* idx_ctr,
+                         float* out, unsigned char* argk, int B, int C, int N, int M, int k, ge_stream_t stream);
+/* dx [B,C,N] overwritten; dy [B,C,M] must be zero-filled by the caller (NULL for a self graph:
+ * neighbour gradients are accumulated into dx). */
+int ge_mrconv_gather_bwd(const float* dout, const long long* idx_nbr, const long long* idx_ctr,
+                         const unsigned char* argk, float* dx, float* dy,
+                         int B, int C, int N, int M, int k, ge_stream_t stream);
+
+/* ---- K6: TGCN pyramid pooling + concat ------------------------------------------------------
+ * avg_pool2d(r) per level + channel concat of TGCN.DyGraphConv2d.forward (models/TGCN.py:62-70),
+ * hoisted out of the time loop.  `in`: NHWC-dense frames [H,W,C] `frame_stride` elements apart;
+ * out fp32 [frames, H/r, W/r, Ctot] (channels_last), this level fills channels [coff, coff+C). */
+int ge_tgcn_pool_concat_fwd(const void* in, long long frame_stride, float* out, int dtype,
+                            long long frames, int H, int W, int C, int r, int Ctot, int coff, ge_stream_t stream);
+int ge_tgcn_pool_concat_bwd(const float* dout, void* din, int dtype,
+                            long long frames, int H, int W, int C, int r, int Ctot, int coff, ge_stream_t stream);
+
+/* ---- K7: FPN top-down / semantic head glue (NHWC feature maps, dtype = GE_DTYPE_*) ---------
+ * (i) out = bilinear_up(top -> HxW, align_corners=True) + lateral   (models/fpnseg.py:371-388);
+ *     lateral may be NULL (plain _upsample, :358-359).  top [N,h,w,C], lateral/out [N,H,W,C]. */
+int ge_upsample_add_fwd(const void* top, const void* lateral, void* out, int dtype,
+                        int N, int h, int w, int H, int W, int C, ge_stream_t stream);
+/* adjoint of the up-sampling: dtop [N,h,w,C] from dout [N,H,W,C] (d lateral = dout). */
+int ge_upsample_bwd(const void* dout, void* dtop, int dtype,
+                    int N, int h, int w, int H, int W, int C, ge_stream_t stream);
+/* (ii) GroupNorm(C,C)+ReLU+_upsample (fpnseg.py:428-442).  Per-(n,c) mean / rstd over HW: */
+int ge_chan_stats(const void* x, float* mean, float* rstd, int dtype,
+                  int N, int HW, int C, float eps, ge_stream_t stream);
+/* out [N,H,W,C] = bilinear_up(relu((x-mean)*rstd*gamma+beta)); x [N,h,w,C]; (h,w)==(H,W) = identity. */
+int ge_gn_relu_upsample_fwd(const void* x, const float* mean, const float* rstd,
+                            const float* gamma, const float* beta, void* out, int dtype,
+                            int N, int h, int w, int H, int W, int C, ge_stream_t stream);
+/* dx [N,h,w,C]; dyh fp32 scratch [N,h,w,C]; S1,S2 fp32 [N,C]: dbeta = sum_n S1, dgamma = sum_n S2. */
+int ge_gn_relu_upsample_bwd(const void* dout, const void* x, const float* mean, const float* rstd,
+                            const float* gamma, const float* beta, float* dyh, float* S1, float* S2,
+                            void* dx, int dtype, int N, int h, int w, int H, int W, int C, ge_stream_t stream);
+/* (iii) logits = bilinear_up_x4(conv3(s2+s3+s4+s5))  (fpnseg.py:444).  s* [N,h,w,C]; W3 [nc,C],
+ *       b3 [nc]; q fp32 [N,h,w,nc] (conv3 output before up-sampling); logits fp32 NCHW [N,nc,H,W]. */
+int ge_seg_tail_fwd(const void* s2, const void* s3, const void* s4, const void* s5,
+                    const float* W3, const float* b3, float* q, float* logits, int dtype,
+                    int N, int h, int w, int H, int W, int C, int nc, ge_stream_t stream);
+/* ds [N,h,w,C] is the gradient of every branch; dW3 [nc,C], db3 [nc] must be zero-filled. */
+int ge_seg_tail_bwd(const float* dlogits, const void* s2, const void* s3, const void* s4, const void* s5,
+                    const float* W3, float* dq, void* ds, float* dW3, float* db3, int dtype,
+                    int N, int h, int w, int H, int W, int C, int nc, ge_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHECHO_B200_H */
