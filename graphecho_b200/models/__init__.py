@@ -1,0 +1,1 @@
+"""Host-side mirror of the reference's `models` package (same module and class names)."""

@@ -1,0 +1,48 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/graphecho_b200.h declares
+(no compute calls: there is no GPU in the build container)."""
+import ctypes
+
+import pytest
+import torch
+
+from graphecho_b200 import _cabi
+
+
+def test_library_exports_every_header_symbol():
+    names = _cabi.header_symbols()
+    assert len(names) >= 20
+    handle = ctypes.CDLL(str(_cabi.LIB_PATH))
+    missing = [n for n in names if not hasattr(handle, n)]
+    assert not missing, f"header declares symbols the .so does not export: {missing}"
+
+
+def test_bindings_cover_header():
+    names = set(_cabi.header_symbols())
+    bound = set(_cabi._SIGNATURES)
+    assert names == bound, f"unbound: {sorted(names - bound)}  stale: {sorted(bound - names)}"
+
+
+def test_version_and_error_text():
+    lib = _cabi.lib()
+    assert lib.ge_version() == 1
+    assert isinstance(_cabi.last_error(), str)
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from graphecho_b200 import functional as GF
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GF.sinkhorn_rpm_exp(torch.randn(4, 5))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GF.affinity_pairwise(torch.randn(4, 32), torch.randn(5, 32), torch.randn(32), torch.randn(1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GF.knn_graph(torch.randn(1, 8, 16, 1))
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    # null pointers are rejected before any CUDA call
+    lib = _cabi.lib()
+    rc = lib.ge_affinity_pairwise_fwd(None, None, None, None, None, 1, 4, 4, 32, None)
+    assert rc < 0 and "null" in _cabi.last_error()
+    assert lib.ge_sinkhorn_rpm_cluster_size(250, 250, 0) == 8
+    assert lib.ge_sinkhorn_rpm_cluster_size(6, 6, 0) == 1
+    assert lib.ge_sinkhorn_rpm_cluster_size(4000, 4000, 0) == -1

@@ -1,0 +1,329 @@
+"""GPU: every C-ABI kernel against the CPU oracle (oracle/*.py) on seeded inputs, and against
+the golden fixtures generated from the reference.  Integer outputs are bit-exact; fp32 outputs
+use the tolerances written at each assert (fp32 re-association round-off)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from graphecho_b200 import functional as GF
+from oracle import graph_ops as G, vig_ops as V
+from oracle.params import make_params
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, rtol=1e-4, atol=1e-5):
+    torch.testing.assert_close(a.detach().cpu().float(), b.detach().cpu().float(), rtol=rtol, atol=atol)
+
+
+def _affinity_AB(X, Y, p, pre=""):
+    """Separable operands of the affinity MLP (the caller-side dense projections)."""
+    W1 = p[pre + "fc_M.0.weight"]
+    A = (X @ p[pre + "project_sr.weight"].t()) @ W1[:, :256].t()
+    B = (Y @ p[pre + "project_tg.weight"].t()) @ W1[:, 256:].t() + p[pre + "fc_M.0.bias"]
+    return A, B
+
+
+# ---------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("n1,n2", [(37, 45), (1, 7), (250, 251), (320, 204), (33, 64)])
+def test_affinity_pairwise_vs_oracle(dev, n1, n2):
+    torch.manual_seed(n1 * 1000 + n2)
+    p = make_params("affinity", fill_prefix="node_affinity.")
+    X, Y = torch.randn(n1, 256), torch.randn(n2, 256)
+    ref = G.affinity(X, Y, p).reshape(n1, n2)
+    pd = {k: v.to(dev) for k, v in p.items()}
+    A, B = _affinity_AB(X.to(dev), Y.to(dev), pd)
+    M = GF.affinity_pairwise(A, B, pd["fc_M.2.weight"].view(-1), pd["fc_M.2.bias"])
+    close(M, ref, rtol=1e-4, atol=2e-5)
+
+
+def test_affinity_pairwise_golden_and_grads(dev, golden):
+    g = golden("affinity_sinkhorn")
+    p = {k: v.to(dev).requires_grad_() for k, v in make_params("affinity", fill_prefix="node_affinity.").items()}
+    X, Y = g["X"].to(dev).requires_grad_(), g["Y"].to(dev).requires_grad_()
+    A, B = _affinity_AB(X, Y, p)
+    M = GF.affinity_pairwise(A, B, p["fc_M.2.weight"].view(-1), p["fc_M.2.bias"])
+    close(M, g["M"], rtol=1e-4, atol=2e-5)
+    P = GF.sinkhorn_rpm_exp(M, 20, True)
+    close(P, g["P"], rtol=5e-4, atol=1e-6)
+    (P * g["W"].to(dev)).sum().backward()
+    close(X.grad, g["dX"], rtol=2e-3, atol=2e-6)
+    close(Y.grad, g["dY"], rtol=2e-3, atol=2e-6)
+    close(p["fc_M.2.weight"].grad, g["dw2"], rtol=2e-3, atol=2e-6)
+    close(p["fc_M.2.bias"].grad, g["db2"], rtol=2e-3, atol=2e-6)
+    close(p["fc_M.0.weight"].grad[:8], g["dfc0"], rtol=2e-3, atol=2e-6)
+    close(p["project_sr.weight"].grad[:8], g["dPs"], rtol=2e-3, atol=2e-6)
+
+
+def test_affinity_pairwise_batched(dev):
+    torch.manual_seed(3)
+    A, B = torch.randn(5, 70, 512, device=dev), torch.randn(5, 90, 512, device=dev)
+    w2, b2 = torch.randn(512, device=dev) * 0.05, torch.randn(1, device=dev)
+    M = GF.affinity_pairwise(A, B, w2, b2)
+    ref = (torch.relu(A[:, :, None, :] + B[:, None, :, :]) * w2).sum(-1) + b2
+    close(M, ref, rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("n1,n2,cs", [(37, 45, 0), (6, 6, 0), (1, 9, 0), (250, 251, 0), (320, 204, 0),
+                                      (100, 100, 1), (100, 100, 2), (100, 100, 4), (100, 101, 8), (130, 97, 16),
+                                      (318, 318, 0)])
+def test_sinkhorn_rpm_fwd_bwd_vs_oracle(dev, n1, n2, cs):
+    torch.manual_seed(n1 + 7 * n2 + cs)
+    M = torch.randn(n1, n2) * 1.7 + 0.3
+    W = torch.randn(n1, n2)
+    Mo = M.clone().requires_grad_()
+    Po = G.sinkhorn_rpm_exp(Mo, 20, True)
+    (Po * W).sum().backward()
+    Md = M.to(dev).requires_grad_()
+    Pd = GF.sinkhorn_rpm_exp(Md, 20, True, cs)
+    close(Pd, Po, rtol=5e-4, atol=1e-6)
+    (Pd * W.to(dev)).sum().backward()
+    close(Md.grad, Mo.grad, rtol=5e-3, atol=2e-6)
+
+
+@pytest.mark.parametrize("iters", [0, 1, 5])
+def test_sinkhorn_rpm_plain_and_batched(dev, iters, golden):
+    torch.manual_seed(iters)
+    M = torch.randn(4, 20, 31) * 2
+    ref = G.sinkhorn_rpm(M, iters, True).exp()
+    out = GF.sinkhorn_rpm_exp(M.to(dev), iters, False)
+    close(out, ref, rtol=5e-4, atol=1e-6)
+    if iters == 5:
+        g = golden("affinity_sinkhorn")
+        close(GF.sinkhorn_rpm_exp(g["Mraw"].to(dev), 5, False), g["rpm5"].exp(), rtol=5e-4, atol=1e-6)
+
+
+def test_sinkhorn_rpm_properties_at_full_size(dev):
+    """Size-independent properties at the largest GModule shape: rows/cols sum to <= 1 (slack),
+    entries in (0,1), and the slack-completed matrix is doubly stochastic after the column pass."""
+    torch.manual_seed(0)
+    M = torch.randn(64, 320, 318, device=dev)
+    P = GF.sinkhorn_rpm_exp(M, 20, True)
+    assert torch.isfinite(P).all() and (P > 0).all() and (P < 1).all()
+    assert (P.sum(1) <= 1 + 1e-4).all()          # column pass came last: column sums + slack == 1
+    assert (P.sum(2) <= 1 + 2e-2).all()
+    with pytest.raises(RuntimeError, match="does not fit"):
+        GF.sinkhorn_rpm_exp(torch.randn(1500, 1500, device=dev), 20, True)
+
+
+def test_sinkhorn_rpm_outlier_is_stable(dev):
+    """A single huge entry (instance-normed z ~ 100): the log-domain kernel must stay finite."""
+    M = torch.randn(100, 120) * 0.01
+    M[3, 5] = 500.0
+    ref = G.sinkhorn_rpm_exp(M, 20, True)
+    out = GF.sinkhorn_rpm_exp(M.to(dev), 20, True)
+    assert torch.isfinite(out).all()
+    close(out, ref, rtol=1e-3, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------- K5
+def test_sinkhorn_distance_golden(dev, golden):
+    for name, c in golden("sinkhorn_distance").items():
+        x, y = c["x"].to(dev), c["y"].to(dev)
+        if x.dim() == 2:
+            x, y = x[None], y[None]
+        x.requires_grad_(); y.requires_grad_()
+        cost, pi, C, nits = GF.sinkhorn_distance(x, y, c["eps"], c["max_iter"])
+        ref_n = G.sinkhorn_distance(c["x"], c["y"], c["eps"], c["max_iter"], c["reduction"])[3]
+        assert int(nits.item()) == ref_n, name
+        if c["reduction"] == "mean":
+            cost = cost.mean()
+        if c["x"].dim() == 2:
+            cost, pi, C = cost[0], pi[0], C[0]
+        close(C, c["C"], rtol=1e-4, atol=1e-5)
+        close(pi, c["pi"], rtol=2e-3, atol=1e-7)
+        close(cost, c["cost"], rtol=2e-3, atol=1e-6)
+        if "dx" in c:
+            cost.sum().backward()
+            close(x.grad, c["dx"], rtol=5e-3, atol=2e-6)
+            close(y.grad, c["dy"], rtol=5e-3, atol=2e-6)
+
+
+def test_sinkhorn_distance_marginals(dev):
+    """Property: after enough iterations the plan's marginals are uniform."""
+    torch.manual_seed(1)
+    x, y = torch.randn(8, 64, 256, device=dev) * 0.05, torch.randn(8, 64, 256, device=dev) * 0.05
+    cost, pi, C, nits = GF.sinkhorn_distance(x, y, 0.1, 200, thresh=1e-6)
+    close(pi.sum(1), torch.full((8, 64), 1 / 64), rtol=1e-3, atol=1e-6)   # v update came last
+    close(pi.sum(2), torch.full((8, 64), 1 / 64), rtol=5e-2, atol=1e-5)
+    assert (C >= 0).all()
+
+
+# ---------------------------------------------------------------------------------------- K1
+def _check_knn(edge, x, y, k, dilation, rel=None):
+    """Exact where the oracle's ordering is unambiguous; where two candidate distances are within
+    fp32 round-off of each other (|gap| < 2e-6) either order is accepted."""
+    dist = V.knn_distances(x, y, rel)
+    ref = V.dense_dilated_knn(x, y, k, dilation, rel)
+    e = edge.cpu()
+    assert e.shape == ref.shape and e.dtype == torch.int64
+    assert torch.equal(e[1], ref[1])
+    mism = (e[0] != ref[0])
+    if mism.any():
+        d_ours = torch.gather(dist, 2, e[0])
+        d_ref = torch.gather(dist, 2, ref[0])
+        assert ((d_ours - d_ref).abs()[mism] < 2e-6).all(), "k-NN index differs beyond a fp32 near-tie"
+    return float(mism.float().mean())
+
+
+def test_knn_golden(dev, golden):
+    g = golden("vig")
+    x, y, rel = g["x"], g["y"], g["rel"]
+    assert _check_knn(GF.knn_graph(x.to(dev), y.to(dev), 5, 2), x, y, 5, 2) < 0.02
+    assert torch.equal(GF.knn_graph(x.to(dev), y.to(dev), 5, 2).cpu()[1], g["e_xy"][1])
+    assert _check_knn(GF.knn_graph(x.to(dev), None, 9, 1, rel.to(dev)), x, None, 9, 1, rel) < 0.02
+    assert _check_knn(GF.knn_graph(x.to(dev), None, 9, 1), x, None, 9, 1) < 0.02
+
+
+@pytest.mark.parametrize("B,C,N,M,k,d", [(8, 256, 64, 64, 9, 1), (2, 256, 784, 784, 9, 1), (2, 48, 196, 49, 9, 2),
+                                         (1, 32, 70, 65, 9, 5), (3, 16, 10, 130, 3, 1), (1, 256, 4096, 1024, 9, 1)])
+def test_knn_vs_oracle(dev, B, C, N, M, k, d):
+    torch.manual_seed(B + C + N)
+    x = torch.randn(B, C, N, 1)
+    y = torch.randn(B, C, M, 1) if (M != N or B == 8) else None
+    frac = _check_knn(GF.knn_graph(x.to(dev), None if y is None else y.to(dev), k, d), x, y, k, d)
+    assert frac < 0.01
+
+
+def test_knn_all_ties_zero_hidden(dev):
+    """TGCN step 0: hidden == 0 so every key is identical (TGCN.py:230).  Any k distinct keys are a
+    valid answer; ours must be the k lowest indices (documented tie rule)."""
+    x = torch.randn(2, 256, 64, 1, device=dev)
+    y = torch.zeros(2, 256, 64, 1, device=dev)
+    e = GF.knn_graph(x, y, 9, 1).cpu()
+    assert torch.equal(e[0], torch.arange(9).expand(2, 64, 9))
+
+
+# ---------------------------------------------------------------------------------------- K2
+def test_mr_gather_golden(dev, golden):
+    g = golden("vig")
+    p = {k: v.to(dev).requires_grad_() for k, v in make_params("mrconv32_64", fill_prefix="grapher.gconv.").items()}
+    x, y = g["x"].to(dev).requires_grad_(), g["y"].to(dev).requires_grad_()
+    feat = GF.mr_gather(x, g["e_xy"].to(dev), y)
+    close(feat, V.max_relative(g["x"], g["e_xy"], g["y"]), rtol=0, atol=0)
+    o = F.gelu(F.conv2d(feat, p["nn.0.weight"], p["nn.0.bias"], groups=4))
+    close(o, g["mr_out"], rtol=1e-4, atol=1e-5)
+    o.square().sum().backward()
+    close(x.grad, g["mr_dx"], rtol=1e-3, atol=1e-5)
+    close(y.grad, g["mr_dy"], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("self_graph,ident", [(True, True), (False, True), (False, False), (True, False)])
+def test_mr_gather_vs_oracle(dev, self_graph, ident):
+    torch.manual_seed(5)
+    B, C, N, M, k = 3, 40, 130, 130 if self_graph else 77, 9
+    x = torch.randn(B, C, N, 1)
+    y = None if self_graph else torch.randn(B, C, M, 1)
+    e0 = torch.randint(0, M, (B, N, k))
+    e1 = torch.arange(N).view(1, N, 1).expand(B, N, k).contiguous() if ident else torch.randint(0, N, (B, N, k))
+    edge = torch.stack([e0, e1])
+    xo = x.clone().requires_grad_()
+    yo = None if y is None else y.clone().requires_grad_()
+    ref = V.max_relative(xo, edge, yo)
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    xd = x.to(dev).requires_grad_()
+    yd = None if y is None else y.to(dev).requires_grad_()
+    out = GF.mr_gather(xd, edge.to(dev), yd, identity_centre=ident)
+    close(out, ref, rtol=0, atol=0)
+    (out * W.to(dev)).sum().backward()
+    close(xd.grad, xo.grad, rtol=1e-5, atol=1e-5)
+    if y is not None:
+        close(yd.grad, yo.grad, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------- K6
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pool_concat(dev, dtype):
+    torch.manual_seed(9)
+    F_, C = 6, 64
+    lv = [torch.randn(F_, C, s, s) for s in (64, 32, 16, 8)]
+    rs = (8, 4, 2, 1)
+    lo = [t.to(dtype).float().clone().requires_grad_() for t in lv]
+    ref = torch.cat([F.avg_pool2d(t, r, r) if r > 1 else t for t, r in zip(lo, rs)], dim=1)
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    ld = [t.detach().to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_() for t in lv]
+    out = GF.pool_concat(ld, rs)
+    assert out.dtype == torch.float32 and out.shape == ref.shape
+    close(out, ref, rtol=1e-5, atol=1e-5)
+    (out * W.to(dev)).sum().backward()
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    for a, b in zip(ld, lo):
+        close(a.grad, b.grad, rtol=tol, atol=tol)
+    with pytest.raises(RuntimeError, match="pooled sizes differ"):
+        GF.pool_concat([torch.randn(1, 8, 28, 28, device=dev), torch.randn(1, 8, 16, 16, device=dev)], (8, 4))
+
+
+# ---------------------------------------------------------------------------------------- K7
+def _cl(t, dev, dtype=torch.float32):
+    return t.to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("h,H", [(4, 7), (7, 14), (14, 28), (8, 16), (1, 5), (28, 28), (16, 64)])
+def test_upsample_add(dev, h, H):
+    torch.manual_seed(h * 100 + H)
+    top, lat = torch.randn(3, 32, h, h), torch.randn(3, 32, H, H)
+    to, lo = top.clone().requires_grad_(), lat.clone().requires_grad_()
+    ref = F.interpolate(to, size=(H, H), mode="bilinear", align_corners=True) + lo
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    td, ld = _cl(top, dev).requires_grad_(), _cl(lat, dev).requires_grad_()
+    out = GF.upsample_add(td, ld)
+    close(out, ref, rtol=1e-5, atol=1e-5)
+    (out * W.to(dev)).sum().backward()
+    close(td.grad, to.grad, rtol=1e-4, atol=1e-5)
+    close(ld.grad, lo.grad, rtol=0, atol=0)
+
+
+def test_upsample_add_rect_and_bf16(dev):
+    torch.manual_seed(4)
+    top, lat = torch.randn(2, 16, 5, 9), torch.randn(2, 16, 11, 17)
+    ref = F.interpolate(top, size=(11, 17), mode="bilinear", align_corners=True) + lat
+    close(GF.upsample_add(_cl(top, dev), _cl(lat, dev)), ref, rtol=1e-5, atol=1e-5)
+    out = GF.upsample_add(_cl(top, dev, torch.bfloat16), _cl(lat, dev, torch.bfloat16))
+    assert out.dtype == torch.bfloat16
+    close(out, ref, rtol=2e-2, atol=3e-2)
+    close(GF.upsample_bilinear(_cl(top, dev), (11, 17)),
+          F.interpolate(top, size=(11, 17), mode="bilinear", align_corners=True), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("h,H,C", [(4, 28, 256), (7, 28, 256), (14, 28, 128), (28, 28, 128), (8, 64, 128)])
+def test_gn_relu_upsample(dev, h, H, C):
+    torch.manual_seed(h + H + C)
+    x = torch.randn(2, C, h, h) * 1.5 + 0.2
+    gamma, beta = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    xo, go, bo = x.clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    ref = F.interpolate(torch.relu(F.group_norm(xo, C, go, bo, 1e-5)), size=(H, H), mode="bilinear", align_corners=True)
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    xd, gd, bd = _cl(x, dev).requires_grad_(), gamma.to(dev).requires_grad_(), beta.to(dev).requires_grad_()
+    out = GF.gn_relu_upsample(xd, gd, bd, (H, H))
+    close(out, ref, rtol=1e-4, atol=1e-5)
+    (out * W.to(dev)).sum().backward()
+    close(xd.grad, xo.grad, rtol=2e-3, atol=2e-4)
+    close(gd.grad, go.grad, rtol=1e-3, atol=1e-3)
+    close(bd.grad, bo.grad, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("nc,h", [(1, 28), (2, 28), (4, 64), (3, 16)])
+def test_seg_tail(dev, nc, h):
+    torch.manual_seed(nc * 10 + h)
+    C = 128
+    s = [torch.relu(torch.randn(2, C, h, h)) for _ in range(4)]
+    W3, b3 = torch.randn(nc, C, 1, 1) * 0.1, torch.randn(nc) * 0.1
+    so = [t.clone().requires_grad_() for t in s]
+    Wo, bo = W3.clone().requires_grad_(), b3.clone().requires_grad_()
+    ref = F.interpolate(F.conv2d(so[0] + so[1] + so[2] + so[3], Wo, bo), size=(4 * h, 4 * h), mode="bilinear", align_corners=True)
+    G_ = torch.randn_like(ref)
+    (ref * G_).sum().backward()
+    sd = [_cl(t, dev).requires_grad_() for t in s]
+    Wd, bd = W3.to(dev).requires_grad_(), b3.to(dev).requires_grad_()
+    out = GF.seg_tail(*sd, Wd, bd, 4)
+    close(out, ref, rtol=1e-4, atol=1e-4)
+    (out * G_.to(dev)).sum().backward()
+    for a, b in zip(sd, so):
+        close(a.grad, b.grad, rtol=1e-3, atol=1e-4)
+    close(Wd.grad, Wo.grad, rtol=1e-3, atol=1e-2)
+    close(bd.grad, bo.grad, rtol=1e-3, atol=1e-2)

@@ -1,0 +1,242 @@
+"""GPU: the drop-in modules (graphecho_b200.models / utils) against the golden fixtures produced by
+the unmodified reference, with identical (name-keyed) weights: outputs, every loss-dict entry,
+gradients and running statistics.  fp32 path: TF32 is off (conftest), tolerances are fp32
+re-association round-off; indices / labels are exact."""
+import contextlib
+import io
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from graphecho_b200 import synth
+from graphecho_b200.models import fpnseg, graph_matching, TGCN as tgcn_mod, vig, affinity_layer, transformer
+from graphecho_b200.utils.sinkhorn_distance import SinkhornDistance
+from graphecho_b200.utils.losses import DiceLoss
+from oracle.detfill import fill_module
+from oracle import fpn_ops as FP
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, rtol=1e-4, atol=1e-5):
+    torch.testing.assert_close(a.detach().cpu().float(), b.detach().cpu().float(), rtol=rtol, atol=atol)
+
+
+def relclose(a, b, tol):
+    """Relative Frobenius-norm error: the right yard-stick for deep-network outputs and gradients,
+    where fp32 round-off of a different (cuDNN vs MKL) summation order is amplified layer by layer
+    (train-mode BatchNorm over 32 samples at the 4x4 level amplifies it most)."""
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    err = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    assert err < tol, f"relative error {err:.3e} >= {tol:.1e}"
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def no_dropout(m):
+    for s in m.modules():
+        if isinstance(s, torch.nn.Dropout):
+            s.p = 0.0
+    return m
+
+
+def test_affinity_attention_modules(dev, golden):
+    g = golden("affinity_sinkhorn")
+    A = fill_module(affinity_layer.Affinity(256), prefix="node_affinity.").to(dev)
+    close(A(g["X"].to(dev), g["Y"].to(dev)), g["M"], rtol=1e-4, atol=2e-5)
+    a = golden("attention")
+    att = fill_module(transformer.MultiHeadAttention(256, 1, dropout=0.1, version="v2"), prefix="intra_domain_graph.").to(dev).eval()
+    out, w = att(a["key"].to(dev), a["key"].to(dev), a["query"].to(dev))
+    close(out, a["out"], rtol=1e-4, atol=1e-5)
+    close(w, a["attn"], rtol=1e-4, atol=1e-7)
+
+
+def test_forward_aff_and_qu(dev, golden):
+    g = golden("forward_aff")
+    gm = fill_module(quiet(graph_matching.GModule, 256, 3, dev)).to(dev)
+    a, b = g["n1"].to(dev).requires_grad_(), g["n2"].to(dev).requires_grad_()
+    loss, Mn = gm._forward_aff(a, b, g["l1"].to(dev), g["l2"].to(dev))
+    qu = gm._forward_qu(g["e1"].to(dev), g["e2"].to(dev), Mn)
+    close(Mn, g["Mn"], rtol=5e-4, atol=1e-6)
+    close(loss, g["loss"], rtol=1e-4, atol=1e-6)
+    close(qu, g["qu"], rtol=1e-4, atol=1e-7)
+    (loss + qu).backward()
+    close(a.grad, g["dn1"], rtol=5e-3, atol=1e-7)
+    close(b.grad, g["dn2"], rtol=5e-3, atol=1e-7)
+
+
+def test_sinkhorn_distance_module(dev, golden):
+    for name, c in golden("sinkhorn_distance").items():
+        m = SinkhornDistance(c["eps"], c["max_iter"], c["reduction"])
+        x, y = c["x"].to(dev).requires_grad_(), c["y"].to(dev).requires_grad_()
+        cost, pi, C = m(x, y)
+        assert cost.shape == c["cost"].shape and pi.shape == c["pi"].shape
+        close(cost, c["cost"], rtol=2e-3, atol=1e-6)
+        close(pi, c["pi"], rtol=2e-3, atol=1e-7)
+        close(C, c["C"], rtol=1e-4, atol=1e-5)
+
+
+def test_grapher_and_mrconv(dev, golden):
+    g = golden("vig")
+    mr = fill_module(vig.MRConv2d(32, 64, "gelu", None, True), prefix="grapher.gconv.").to(dev)
+    edge = vig.DenseDilatedKnnGraph(5, 2)(g["x"].to(dev), g["y"].to(dev))
+    assert (edge.cpu() != g["e_xy"]).float().mean() < 0.02
+    x, y = g["x"].to(dev).requires_grad_(), g["y"].to(dev).requires_grad_()
+    e = g["e_xy"].to(dev)
+    e._ge_identity_centre = True
+    o = mr(x, e, y)
+    close(o, g["mr_out"], rtol=1e-4, atol=1e-5)
+    for r in (1, 2):
+        c = g[f"grapher_r{r}"]
+        gr = fill_module(vig.Grapher(32, 5, 1, "mr", "gelu", "batch", True, False, 0.0, r, 64, 0.0, False),
+                         prefix=f"grapher_r{r}.").to(dev).train()
+        xin = c["x"].to(dev).requires_grad_()
+        out = gr(xin)
+        close(out, c["out"], rtol=1e-3, atol=1e-4)
+        out.square().mean().backward()
+        close(xin.grad, c["dx"], rtol=5e-3, atol=1e-5)
+        close(gr.fc1[0].weight.grad, c["dfc1"], rtol=5e-3, atol=1e-5)
+        close(gr.fc2[1].running_mean, c["rm"], rtol=1e-4, atol=1e-5)
+        close(gr.fc1[1].running_var, c["rv"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("bb,nc,hw", [("resnet", 1, 112), ("VGG16", 3, 64)])
+def test_fpn_matches_reference(dev, golden, bb, nc, hw):
+    g = golden("fpn")
+    x = g[f"{bb}_x"].to(dev)
+    for mode in ("eval", "train"):
+        rec = g[f"{bb}_{mode}"]
+        net = fill_module(fpnseg.FPN([2, 4, 23, 3], nc, 1, back_bone=bb), scale=0.7).to(dev)
+        net.train(mode == "train")
+        xr = x.clone().requires_grad_(mode == "train")
+        logits, feats = net(xr)
+        assert logits.shape == rec["logits"].shape and logits.dtype == torch.float32
+        # eval: fixed statistics -> 1e-5 relative; train: batch statistics amplify round-off -> 1e-3
+        tol = 2e-5 if mode == "eval" else 1e-3
+        relclose(logits, rec["logits"], tol)
+        relclose(feats[3], rec["p5"], tol)
+        relclose(feats[2], rec["p4"], tol)
+        relclose(feats[0][:, ::16, ::3, ::3], rec["p2_slice"], tol)
+        relclose(feats[1][:, ::16, ::2, ::2], rec["p3_slice"], tol)
+        # bit-exact argmax / threshold masks wherever the reference logit is not within round-off of 0
+        ref = rec["logits"]
+        sure = ref.abs() > (1e-3 if mode == "eval" else 2e-2)
+        assert torch.equal((logits.cpu() > 0)[sure], (ref > 0)[sure])
+        if mode == "train":
+            B = x.shape[0]
+            mask = (synth.disc_masks(B, nc, hw) if nc > 1 else synth.disc_masks(B, 2, hw)[:, 1:2]).to(dev)
+            loss = DiceLoss()(logits, mask) + F.binary_cross_entropy_with_logits(logits, mask)
+            close(loss, rec["loss"], rtol=1e-4, atol=1e-5)
+            loss.backward()
+            relclose(net.conv3.weight.grad, rec["dconv3"], 2e-3)
+            relclose(net.gn1.weight.grad, rec["dgn1"], 2e-3)
+            relclose(net.semantic_branch.weight.grad[:4], rec["dsem"], 1e-2)
+            relclose(net.toplayer.weight.grad[:4, :64], rec["dtop"], 5e-2)
+            relclose(xr.grad, rec["dx"], 2e-1)      # through ~50 train-mode BN layers: ill-conditioned
+            bn = net.back_bone.bn1 if bb == "resnet" else net.back_bone.block_1[1]
+            close(bn.running_mean, rec["bn1_rm"], rtol=1e-4, atol=1e-6)
+            # Dice on the thresholded masks equals the reference's (train_cardiac_uda.py:496-511)
+            d_ours = FP.overlap_metrics(mask.cpu(), (torch.sigmoid(logits.detach().cpu()) > 0.5).float())[1]
+            d_ref = FP.overlap_metrics(mask.cpu(), (torch.sigmoid(ref) > 0.5).float())[1]
+            close(d_ours, d_ref, rtol=1e-4, atol=1e-5)
+
+
+def test_discriminator(dev, golden):
+    d = golden("discriminator")
+    m = fill_module(fpnseg.Discriminator(grad_reverse_lambda=0.02), prefix="dis.").to(dev)
+    a, b = d["fs"].to(dev).requires_grad_(), d["ft"].to(dev).requires_grad_()
+    loss = m((a, b))
+    close(loss, d["loss"], rtol=1e-4, atol=1e-6)
+    loss.backward()
+    close(a.grad, d["dfs"], rtol=5e-3, atol=1e-8)
+    close(b.grad, d["dft"], rtol=5e-3, atol=1e-8)
+    close(m.cls_logits.weight.grad, d["dcls"], rtol=5e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("backend", ["sklearn"])
+def test_gmodule_train_step(dev, golden, backend):
+    g = golden("gmodule")
+    B, hw, nc = g["B"], g["hw"], g["nc"]
+    gm = no_dropout(fill_module(quiet(graph_matching.GModule, 256, nc, dev))).to(dev).train()
+    gm.cluster_backend = backend
+    fs = [f.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_() for f in synth.pyramid(B, hw, seed=21)]
+    ft = [f.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_() for f in synth.pyramid(B, hw, seed=22)]
+    masks, score = synth.disc_masks(B, nc, hw).to(dev), synth.disc_masks(B, nc, hw, shift=6).to(dev)
+    _, (n1, n2), losses = gm(None, (fs, ft), targets=masks, score_maps=score)
+    assert set(losses) == set(g["losses"])
+    assert n1.shape == g["n1"].shape and n2.shape == g["n2"].shape
+    for k in losses:
+        close(losses[k], g["losses"][k], rtol=2e-3, atol=1e-6)
+    close(n1, g["n1"], rtol=2e-3, atol=2e-4)
+    close(n2, g["n2"], rtol=2e-3, atol=2e-4)
+    close(gm.sr_seed, g["sr_seed"], rtol=2e-3, atol=2e-4)
+    close(gm.tg_seed, g["tg_seed"], rtol=2e-3, atol=2e-4)
+    sum(losses.values()).backward()
+    close(fs[3].grad, g["dfs3"], rtol=1e-2, atol=1e-7)
+    close(fs[0].grad.abs().sum(), g["dfs0_abs"], rtol=1e-2, atol=1e-7)
+    close(gm.node_affinity.fc_M[2].weight.grad, g["daff"], rtol=1e-2, atol=1e-7)
+    s = golden("sampler")
+    feats = [f.to(dev) for f in synth.pyramid(B, hw, seed=21)]
+    nodes, labels, weights = gm.graph_generator(gm.compute_locations(feats), feats, gm.find_bbox(masks))
+    assert torch.equal(labels.cpu(), s["labels"])
+    close(nodes.sum(1), s["nodes_sum"], rtol=1e-5, atol=1e-4)
+    assert torch.equal(gm.find_bbox(masks)[1].cpu(), s["boxes"])
+
+
+def test_gmodule_no_nodes_early_return(dev):
+    """num_classes=1: every location is background -> no nodes -> empty loss dict (Appendix A-1)."""
+    gm = quiet(graph_matching.GModule, 256, 1, dev).to(dev).train()
+    feats = [f.to(dev) for f in synth.pyramid(2, 112, seed=1)]
+    m = synth.disc_masks(2, 2, 112)[:, 1:2].to(dev)
+    _, (n1, n2), losses = gm(None, (feats, feats), targets=m, score_maps=m)
+    assert losses == {} and n1.shape[0] == 0
+
+
+@pytest.mark.parametrize("transport", ["node_discriminate", "sinkhorn_distance"])
+def test_tgcn(dev, golden, transport):
+    rec = golden("tgcn")[transport]
+    m = no_dropout(fill_module(quiet(tgcn_mod.TGCN, 256, 256, (3, 8, 8), 10, 10, None, transport))).to(dev).train()
+    feats = [f.to(dev).requires_grad_() for f in synth.clip_pyramid(2, 3, 256, seed=31)]
+    idx = (torch.zeros(1, dtype=torch.long, device=dev), torch.zeros(1, dtype=torch.long, device=dev))
+    losses = m(feats, (rec["src"].to(dev), rec["tgt"].to(dev)), SinkhornDistance(0.1, 5, "mean"),
+               torch.nn.CrossEntropyLoss(), idx, r=[8, 4, 2, 1])
+    assert set(losses) == set(rec["losses"])
+    for k in losses:
+        close(losses[k], rec["losses"][k], rtol=5e-3, atol=1e-6)
+    sum(losses.values()).backward()
+    # sinkhorn transport on LayerNorm-scale nodes has C/eps ~ 5e3 in the exponent: round-off of C is
+    # amplified ~1e3x, in the reference as much as here
+    tol = 1e-4 if transport == "node_discriminate" else 1e-2
+    relclose(feats[3].grad, rec["df3"], tol)
+    close(feats[0].grad.abs().sum(), rec["df0_abs"], rtol=2e-2, atol=1e-8)
+    relclose(m.pos_embed.grad[:, :, :8], rec["dpos"], tol)
+    close(m.grapher.MLP[1].running_mean, rec["mlp_rm"], rtol=1e-4, atol=1e-6)
+    close(m.prediction[1].running_var, rec["pred_rv"], rtol=1e-4, atol=1e-6)
+
+
+def test_tgcn_rejects_112_inputs_like_the_reference(dev):
+    """At 112x112 the pooled sizes are 3,3,3,4 and the reference's torch.cat fails (Appendix A-2)."""
+    m = quiet(tgcn_mod.TGCN, 256, 256, (8, 8, 8), 10, 10).to(dev)
+    feats = [f.to(dev) for f in synth.clip_pyramid(2, 2, 112, seed=3)]
+    with pytest.raises(RuntimeError, match="pooled sizes differ"):
+        m(feats, (torch.randn(5, 256, device=dev), torch.randn(5, 256, device=dev)), None, None, (None, None), r=[8, 4, 2, 1])
+
+
+def test_bf16_autocast_path(dev, golden):
+    """bf16 tensor-core path (config 2): logits within 3e-2 relative of the fp32 reference and
+    >= 99% thresholded-mask agreement."""
+    g = golden("fpn")
+    rec = g["resnet_eval"]
+    net = fill_module(fpnseg.FPN([2, 4, 23, 3], 1, 1, back_bone="resnet"), scale=0.7).to(dev).eval()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, feats = net(g["resnet_x"].to(dev))
+    assert logits.dtype == torch.float32 and feats[0].dtype == torch.bfloat16
+    ref = rec["logits"]
+    rel = (logits.cpu() - ref).norm() / ref.norm()
+    assert rel < 3e-2, rel
+    agree = ((logits.cpu() > 0) == (ref > 0)).float().mean()
+    assert agree > 0.99, agree
