@@ -94,9 +94,39 @@ def stream() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name: str, *args) -> None:
-    """Invoke an int-returning entry point and raise on a non-zero status."""
-    rc = getattr(lib(), name)(*args)
+# Optional per-entry-point timing (bench.py): name -> list of (start_event, end_event, bytes, flops).
+# Events are recorded on the stream the kernels are launched on (torch's current stream).
+_PROFILE: dict | None = None
+
+
+def profile_start() -> None:
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop() -> dict:
+    """-> {name: {"calls", "ms", "bytes", "flops"}} summed over the profiled region (syncs)."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE or {}, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, items in rec.items():
+        out[name] = {"calls": len(items), "ms": sum(a.elapsed_time(b) for a, b, _, _ in items),
+                     "bytes": sum(i[2] for i in items), "flops": sum(i[3] for i in items)}
+    return out
+
+
+def call(name: str, *args, work=(0, 0)) -> None:
+    """Invoke an int-returning entry point and raise on a non-zero status.  `work` = the call's
+    ALGORITHMIC (bytes, flops), used only by the profiler."""
+    if _PROFILE is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib(), name)(*args)
+        b.record()
+        _PROFILE.setdefault(name, []).append((a, b, work[0], work[1]))
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         kind = "argument/shape" if rc < 0 else "CUDA"
         raise GraphEchoNativeError(f"{name} failed ({kind} error {rc}): {last_error()}")

@@ -1,0 +1,236 @@
+"""The GraphEcho UDA training step on the B200-native modules, plus the multi-GPU plumbing.
+
+`UDAEngine.train_step` restates the inner loop of the reference trainers
+(train_cardiac_uda.py:223-325, train_camus_echo.py:206-299): segmentation network on source +
+target frames, Dice+BCE on the source, thresholded target score maps, graph matching, four
+pyramid discriminators, optional ViG Grapher on p2 (112x112 workloads) or TGCN temporal module
+(256x256 clips), one backward, one optimizer step per module group (Adam for the network, SGD for
+the rest, as the reference's config dicts, train_cardiac_uda.py:646-736).
+
+Multi-GPU: one process per GPU, the batch-of-clips axis is sharded (both streams symmetrically),
+no data-path collective; the only exchange is the gradient all-reduce, done as ONE NCCL call over
+a flat fp32 gradient buffer that every parameter's .grad is a view of (no bucket copies), plus
+SyncBatchNorm on the segmentation network as the reference intends (train_cardiac_uda.py:142).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from .models.fpnseg import FPN, Discriminator
+from .models.graph_matching import GModule
+from .models.TGCN import TGCN
+from .models.vig import Grapher
+from .utils.losses import DiceLoss
+from .utils.sinkhorn_distance import SinkhornDistance
+from . import synth
+
+
+@dataclass
+class EngineConfig:
+    backbone: str = "resnet"            # 'resnet' (CAMUS/EchoNet, 112x112) | 'VGG16' (CardiacUDA, 256x256)
+    num_classes: int = 2
+    hw: int = 112
+    bf16: bool = True                   # tensor-core convs under autocast; graph modules stay fp32
+    graph_matching: bool = True
+    discriminator: bool = True
+    vig_grapher: bool = True            # Grapher(256, k=9, 'mr', 'gelu', 'batch') on p2 (config 2)
+    temporal_graph: bool = False        # TGCN on [b,t] clips (256x256 only, Appendix A-2)
+    clip_frames: int = 8
+    sync_bn: bool = True
+    seg_weight: float = 1.0             # train_camus_echo.py:212 uses 0.05
+    lr_net: float = 3e-4
+    lr_aux: float = 2.5e-3
+    weight_decay: float = 1e-4
+    cluster_backend: str = "device"     # GModule.update_seed bipartition: 'device' | 'sklearn'
+    seed: int = 0
+
+
+def shard_range(n_items: int, rank: int, world: int) -> range:
+    """Contiguous, balanced shard of `n_items` clips for `rank` (first ranks take the remainder)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+class FlatGradSync:
+    """All parameters' .grad live in one flat fp32 buffer -> the DDP exchange is a single
+    all-reduce(AVG) per step, no per-bucket copies, no hooks, tolerant of parameters that did not
+    take part in the step (their slice stays zero)."""
+
+    def __init__(self, modules, group=None):
+        self.params = [p for m in modules for p in m.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            p.grad = self._view(p, off)
+            off += p.numel()
+        self.group = group
+
+    def _view(self, p, off):
+        """A gradient view with the parameter's own (dense, possibly channels_last) strides, which is
+        what the fused optimizers require."""
+        return torch.as_strided(self.flat, p.shape, p.stride(), storage_offset=off)
+
+    def zero(self):
+        self.flat.zero_()
+
+    def rebind(self):
+        """Restore the views if an optimizer / user replaced .grad (e.g. set_to_none)."""
+        off = 0
+        for p in self.params:
+            view = self._view(p, off)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
+            off += p.numel()
+
+    def all_reduce(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.div_(dist.get_world_size(self.group))
+
+    @property
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+
+def init_distributed(device_index: int | None = None):
+    """torchrun-style env (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).  Returns (rank, local_rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) if device_index is None else device_index
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, local, world
+
+
+class UDAEngine:
+    def __init__(self, cfg: EngineConfig, device: torch.device, world_size: int = 1):
+        self.cfg, self.device, self.world = cfg, device, world_size
+        torch.manual_seed(cfg.seed)           # identical initial weights on every rank
+        nc = cfg.num_classes
+        self.network = FPN([2, 4, 23, 3], num_classes=nc, in_channel=1, back_bone=cfg.backbone).to(device)
+        self.network = self.network.to(memory_format=torch.channels_last)
+        if world_size > 1 and cfg.sync_bn:
+            self.network = nn.SyncBatchNorm.convert_sync_batchnorm(self.network)
+        self.aux: dict[str, nn.Module] = {}
+        if cfg.graph_matching:
+            gm = GModule(in_channels=256, num_classes=nc, device=device).to(device)
+            gm.cluster_backend = cfg.cluster_backend
+            self.aux["Graph"] = gm
+        if cfg.discriminator and cfg.graph_matching:
+            for lvl in ("p2", "p3", "p4", "p5"):
+                self.aux[f"Dis_{lvl.upper()}"] = Discriminator(grad_reverse_lambda=0.02).to(device).to(
+                    memory_format=torch.channels_last)
+        if cfg.vig_grapher:
+            self.aux["Grapher"] = Grapher(256, 9, 1, "mr", "gelu", "batch", True, False, 0.0, 1,
+                                          (cfg.hw // 4) ** 2, 0.0, False).to(device)
+        if cfg.temporal_graph:
+            self.aux["TGCN"] = TGCN(256, 256, (cfg.clip_frames, 8, 8), 10, 10).to(device)
+        self.sinkhorn = SinkhornDistance(eps=0.1, max_iter=5, reduction="mean")
+        self.dice = DiceLoss()
+        self.ce = nn.CrossEntropyLoss()
+        modules = [self.network, *self.aux.values()]
+        for m in modules:
+            m.train()
+        self.grads = FlatGradSync(modules)
+        self.opt = {"Net": torch.optim.Adam(self.network.parameters(), lr=cfg.lr_net, betas=(0.9, 0.999),
+                                            weight_decay=cfg.weight_decay, fused=device.type == "cuda")}
+        for name, m in self.aux.items():
+            self.opt[name] = torch.optim.SGD(m.parameters(), lr=cfg.lr_aux, momentum=0.9,
+                                             weight_decay=cfg.weight_decay, fused=device.type == "cuda")
+
+    # ------------------------------------------------------------------------------------------
+    def seg_loss(self, logits, masks):
+        return self.dice(logits, masks) + F.binary_cross_entropy_with_logits(logits, masks)
+
+    def forward_losses(self, frames_src, masks_src, frames_tgt, clips_shape=None):
+        """frames_* [F,1,H,W] (fp32, device), masks_src [F,nc,H,W] one-hot.  Returns the loss dict."""
+        cfg = self.cfg
+        ns = frames_src.shape[0]
+        losses = {}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16):
+            logits, feats = self.network(torch.cat([frames_src, frames_tgt], dim=0))
+        pred_s, pred_t = logits[:ns], logits[ns:]
+        losses["seg_loss"] = cfg.seg_weight * self.seg_loss(pred_s, masks_src)
+        if not cfg.graph_matching:
+            return losses
+        if cfg.vig_grapher:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16):
+                feats = [self.aux["Grapher"](feats[0])] + list(feats[1:])
+        fs, ft = [f[:ns] for f in feats], [f[ns:] for f in feats]
+        score_maps = torch.where(torch.sigmoid(pred_t) > 0.5, 1, 0)                # train_cardiac_uda.py:235
+        (fs, ft), nodes, mid = self.aux["Graph"](None, (fs, ft), targets=masks_src, score_maps=score_maps)
+        losses.update(mid)
+        if cfg.discriminator:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16):
+                for i, lvl in enumerate(("p2", "p3", "p4", "p5")):
+                    losses[f"loss_adv_{lvl}"] = 0.1 * self.aux[f"Dis_{lvl.upper()}"]((fs[i], ft[i]))
+        if cfg.temporal_graph and clips_shape is not None and nodes[0].numel() > 0 and nodes[0].dim() == 2:
+            b, t = clips_shape                                                      # train_cardiac_uda.py:300-304
+            graph_features = [f.reshape(b, t, *f.shape[1:]) for f in feats]
+            tl = self.aux["TGCN"](graph_features, (nodes[0].detach(), nodes[1].detach()), self.sinkhorn, self.ce,
+                                  (None, None), r=[8, 4, 2, 1])
+            losses["temporal_graph_loss"] = sum(tl.values())
+        return losses
+
+    def train_step(self, frames_src, masks_src, frames_tgt, clips_shape=None):
+        self.grads.zero()
+        losses = self.forward_losses(frames_src, masks_src, frames_tgt, clips_shape)
+        total = sum(losses.values())
+        total.backward()
+        self.grads.rebind()
+        self.grads.all_reduce()
+        for opt in self.opt.values():
+            opt.step()
+        return total.detach(), {k: v.detach() for k, v in losses.items()}
+
+    @torch.no_grad()
+    def predict(self, frames):
+        self.network.eval()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.cfg.bf16):
+            logits, _ = self.network(frames)
+        self.network.train()
+        return logits
+
+
+def make_batch(cfg: EngineConfig, n_clips: int, frames: int, rank: int = 0, world: int = 1, seed: int = 0,
+               pin: bool = False):
+    """Synthetic step input on the HOST in the trainers' layout: clips [b,1,H,W,t] (first half of the
+    clips = source stream, second half = target) + one-hot source masks [b/2 * t, nc, H, W].
+    Weak scaling: every rank draws its own `n_clips` clips (different seed per rank)."""
+    x = synth.clips(n_clips, cfg.hw, frames, seed=seed + 1000 * rank)
+    ns = n_clips // 2
+    masks = synth.disc_masks(ns * frames, cfg.num_classes, cfg.hw)
+    if pin and torch.cuda.is_available():
+        x, masks = x.pin_memory(), masks.pin_memory()
+    return x, masks
+
+
+def split_streams(clips_dev: torch.Tensor):
+    """[b,1,H,W,t] on device -> (source frames, target frames, (b, t)); clip-major frame order."""
+    b, c, h, w, t = clips_dev.shape
+    frames = synth.flatten_clips(clips_dev)
+    ns = (b // 2) * t
+    return frames[:ns], frames[ns:], (b, t)

@@ -50,7 +50,8 @@ class _AffinityPairwise(Function):
         N2 = B3.shape[1]
         M = torch.empty((batch, N1, N2), device=A.device, dtype=torch.float32)
         call("ge_affinity_pairwise_fwd", ptr(A3), ptr(B3), ptr(w2c), ptr(b2c), ptr(M),
-             batch, N1, N2, H, stream())
+             batch, N1, N2, H, stream(),
+             work=(4 * batch * (H * (N1 + N2) + N1 * N2), 3 * batch * H * N1 * N2))
         ctx.save_for_backward(A3, B3, w2c)
         ctx.squeeze = squeeze
         ctx.shapes = (w2.shape, b2.shape)
@@ -69,7 +70,8 @@ class _AffinityPairwise(Function):
         nbytes = _cabi.lib().ge_affinity_pairwise_bwd_workspace_bytes(batch, N1, N2, H)
         ws = torch.empty(max(nbytes, 4), device=A3.device, dtype=torch.uint8)
         call("ge_affinity_pairwise_bwd", ptr(A3), ptr(B3), ptr(w2c), ptr(dM3), ptr(dA), ptr(dB),
-             ptr(dw2), ptr(db2), ptr(ws), c_size_t(ws.numel()), batch, N1, N2, H, stream())
+             ptr(dw2), ptr(db2), ptr(ws), c_size_t(ws.numel()), batch, N1, N2, H, stream(),
+             work=(4 * batch * (2 * H * (N1 + N2) + N1 * N2), 8 * batch * H * N1 * N2))
         if ctx.squeeze:
             dA, dB = dA[0], dB[0]
         return dA, dB, dw2.view(ctx.shapes[0]), db2.view(ctx.shapes[1])
@@ -94,7 +96,8 @@ class _SinkhornRpm(Function):
         hist_c = torch.empty((batch, max(n_iters, 1), N2), device=dev, dtype=torch.float32)
         stats = torch.empty((batch, 4), device=dev, dtype=torch.float32)
         call("ge_sinkhorn_rpm_fwd", ptr(M3), ptr(P), ptr(hist_r), ptr(hist_c), ptr(stats),
-             batch, N1, N2, int(n_iters), int(bool(instnorm)), int(cluster_size), stream())
+             batch, N1, N2, int(n_iters), int(bool(instnorm)), int(cluster_size), stream(),
+             work=(batch * (8 * N1 * N2 + 4 * int(n_iters) * (N1 + N2)), batch * N1 * N2 * (8 * int(n_iters) + 6)))
         ctx.save_for_backward(M3, hist_r, hist_c, stats)
         ctx.cfg = (int(n_iters), int(bool(instnorm)), int(cluster_size), squeeze)
         return P[0] if squeeze else P
@@ -108,7 +111,8 @@ class _SinkhornRpm(Function):
         G3 = _f32c(G if not squeeze else G.unsqueeze(0))
         dM = torch.empty_like(M3)
         call("ge_sinkhorn_rpm_bwd", ptr(M3), ptr(G3), ptr(hist_r), ptr(hist_c), ptr(stats), ptr(dM),
-             batch, N1, N2, n_iters, instnorm, cluster_size, stream())
+             batch, N1, N2, n_iters, instnorm, cluster_size, stream(),
+             work=(batch * (12 * N1 * N2 + 4 * n_iters * (N1 + N2)), batch * N1 * N2 * (12 * n_iters + 10)))
         return (dM[0] if squeeze else dM), None, None, None
 
 
@@ -136,7 +140,8 @@ class _SinkhornDistance(Function):
         nits = torch.zeros(1, device=dev, dtype=torch.int32)
         call("ge_sinkhorn_distance_fwd", ptr(x3), ptr(y3), ptr(C), ptr(pi), ptr(cost), ptr(hist_u),
              ptr(hist_v), ptr(err), ptr(nits), B, P1, P2, D, c_float(eps), int(max_iter),
-             c_double(thresh), stream())
+             c_double(thresh), stream(),
+             work=(4 * B * D * (P1 + P2) + 8 * B * P1 * P2, 3 * B * P1 * P2 * D + 10 * B * P1 * P2 * int(max_iter)))
         ctx.save_for_backward(x3, y3, C, hist_u, hist_v, nits)
         ctx.cfg = (float(eps), int(max_iter))
         ctx.mark_non_differentiable(pi, C, nits)
@@ -153,7 +158,8 @@ class _SinkhornDistance(Function):
         dC = torch.empty_like(C)
         dx, dy = torch.empty_like(x3), torch.empty_like(y3)
         call("ge_sinkhorn_distance_bwd", ptr(x3), ptr(y3), ptr(C), ptr(hist_u), ptr(hist_v), ptr(nits),
-             ptr(g), ptr(dC), ptr(dx), ptr(dy), B, P1, P2, D, c_float(eps), max_iter, stream())
+             ptr(g), ptr(dC), ptr(dx), ptr(dy), B, P1, P2, D, c_float(eps), max_iter, stream(),
+             work=(8 * B * D * (P1 + P2) + 8 * B * P1 * P2, 4 * B * P1 * P2 * D + 20 * B * P1 * P2 * max_iter))
         return dx, dy, None, None, None
 
 
@@ -184,7 +190,8 @@ def knn_graph(x, y=None, k=9, dilation=1, relative_pos=None):
     nbytes = _cabi.lib().ge_knn_graph_workspace_bytes(B, C, N, M)
     ws = torch.empty(max(nbytes, 4), device=x.device, dtype=torch.uint8)
     call("ge_knn_graph", ptr(x3), ptr(y3), ptr(rel), ptr(out), ptr(ws), c_size_t(ws.numel()),
-         B, C, N, M, int(k), int(dilation), stream())
+         B, C, N, M, int(k), int(dilation), stream(),
+         work=(4 * B * C * (N + M) + 16 * B * N * int(k), 2 * B * N * M * C))
     return out
 
 
@@ -206,7 +213,8 @@ class _MRGather(Function):
         out = torch.empty((B, 2 * C, N), device=x.device, dtype=torch.float32)
         argk = torch.empty((B, C, N), device=x.device, dtype=torch.uint8)
         call("ge_mrconv_gather_fwd", ptr(x3), ptr(y3), ptr(i0), ptr(i1), ptr(out), ptr(argk),
-             B, C, N, M, k, stream())
+             B, C, N, M, k, stream(),
+             work=(4 * B * C * (N + (M if y is not None else 0)) + 8 * B * N * k + 9 * B * C * N, 2 * B * C * N * k))
         ctx.save_for_backward(i0, i1 if i1 is not None else i0, argk)
         ctx.cfg = (B, C, N, M, k, i1 is not None, y is not None, x.shape, None if y is None else y.shape)
         ctx.mark_non_differentiable(argk)
@@ -221,7 +229,8 @@ class _MRGather(Function):
         dx = torch.empty((B, C, N), device=d.device, dtype=torch.float32)
         dy = torch.zeros((B, C, M), device=d.device, dtype=torch.float32) if has_y else None
         call("ge_mrconv_gather_bwd", ptr(d), ptr(i0), ptr(i1 if has_ctr else None), ptr(argk), ptr(dx), ptr(dy),
-             B, C, N, M, k, stream())
+             B, C, N, M, k, stream(),
+             work=(13 * B * C * N + 8 * B * N * k + (4 * B * C * M if has_y else 0), 2 * B * C * N))
         return dx.view(xshape), (dy.view(yshape) if has_y else None), None, None
 
 
@@ -257,7 +266,8 @@ class _PoolConcat(Function):
                 raise _cabi.GraphEchoNativeError(
                     f"pooled sizes differ: level {tuple(t.shape)} with r={r} vs {(Ho, Wo)} (TGCN.py:64-70 would fail in torch.cat)")
             call("ge_tgcn_pool_concat_fwd", ptr(t), c_longlong(H * W * C), ptr(out), _dtype_code(t),
-                 c_longlong(F_), H, W, C, int(r), Ctot, coff, stream())
+                 c_longlong(F_), H, W, C, int(r), Ctot, coff, stream(),
+                 work=(F_ * C * (H * W * t.element_size() + 4 * Ho * Wo), F_ * C * H * W))
             meta.append((t.shape, t.dtype, int(r), coff))
             coff += C
         ctx.meta = meta
@@ -272,7 +282,8 @@ class _PoolConcat(Function):
         for shape, dtype, r, coff in ctx.meta:
             _, C, H, W = shape
             g = torch.empty(shape, device=d.device, dtype=dtype, memory_format=torch.channels_last)
-            call("ge_tgcn_pool_concat_bwd", ptr(d), ptr(g), _dtype_code(g), c_longlong(F_), H, W, C, r, Ctot, coff, stream())
+            call("ge_tgcn_pool_concat_bwd", ptr(d), ptr(g), _dtype_code(g), c_longlong(F_), H, W, C, r, Ctot, coff, stream(),
+                 work=(F_ * C * (H * W * g.element_size() + 4 * (H // r) * (W // r)), F_ * C * H * W))
             grads.append(g)
         return (None, *grads)
 
@@ -294,7 +305,9 @@ class _UpsampleAdd(Function):
         if lateral is not None:
             lat = _nhwc_view(lateral.to(t.dtype))
         out = torch.empty((N, C, H, W), device=t.device, dtype=t.dtype, memory_format=torch.channels_last)
-        call("ge_upsample_add_fwd", ptr(t), ptr(lat), ptr(out), _dtype_code(t), N, h, w, H, W, C, stream())
+        es = t.element_size()
+        call("ge_upsample_add_fwd", ptr(t), ptr(lat), ptr(out), _dtype_code(t), N, h, w, H, W, C, stream(),
+             work=(N * C * es * (h * w + (2 if lat is not None else 1) * H * W), 8 * N * C * H * W))
         ctx.cfg = (N, C, h, w, H, W, lateral is not None)
         return out
 
@@ -304,7 +317,8 @@ class _UpsampleAdd(Function):
         N, C, h, w, H, W, has_lat = ctx.cfg
         d = _nhwc_view(dout)
         dtop = torch.empty((N, C, h, w), device=d.device, dtype=d.dtype, memory_format=torch.channels_last)
-        call("ge_upsample_bwd", ptr(d), ptr(dtop), _dtype_code(d), N, h, w, H, W, C, stream())
+        call("ge_upsample_bwd", ptr(d), ptr(dtop), _dtype_code(d), N, h, w, H, W, C, stream(),
+             work=(N * C * d.element_size() * (h * w + H * W), 2 * N * C * H * W))
         return dtop, (d if has_lat else None), None
 
 
@@ -328,10 +342,12 @@ class _GnReluUpsample(Function):
         mean = torch.empty((N, C), device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         code = _dtype_code(xc)
-        call("ge_chan_stats", ptr(xc), ptr(mean), ptr(rstd), code, N, h * w, C, c_float(eps), stream())
+        es = xc.element_size()
+        call("ge_chan_stats", ptr(xc), ptr(mean), ptr(rstd), code, N, h * w, C, c_float(eps), stream(),
+             work=(N * C * h * w * es, 3 * N * C * h * w))
         out = torch.empty((N, C, H, W), device=x.device, dtype=xc.dtype, memory_format=torch.channels_last)
         call("ge_gn_relu_upsample_fwd", ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(out), code,
-             N, h, w, H, W, C, stream())
+             N, h, w, H, W, C, stream(), work=(N * C * es * (h * w + H * W), 12 * N * C * H * W))
         ctx.save_for_backward(xc, mean, rstd, g, b)
         ctx.cfg = (N, C, h, w, H, W, gamma.dtype, beta.dtype)
         return out
@@ -347,7 +363,8 @@ class _GnReluUpsample(Function):
         S2 = torch.empty_like(S1)
         dx = torch.empty_like(xc)
         call("ge_gn_relu_upsample_bwd", ptr(d), ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dyh),
-             ptr(S1), ptr(S2), ptr(dx), _dtype_code(xc), N, h, w, H, W, C, stream())
+             ptr(S1), ptr(S2), ptr(dx), _dtype_code(xc), N, h, w, H, W, C, stream(),
+             work=(N * C * (xc.element_size() * (H * W + 3 * h * w) + 8 * h * w), 20 * N * C * H * W))
         return dx, S2.sum(0).to(gdt), S1.sum(0).to(bdt), None, None
 
 
@@ -370,7 +387,8 @@ class _SegTail(Function):
         q = torch.empty((N, h, w, nc), device=a.device, dtype=torch.float32)
         logits = torch.empty((N, nc, H, W), device=a.device, dtype=torch.float32)
         call("ge_seg_tail_fwd", ptr(a), ptr(b), ptr(c), ptr(d), ptr(Wm), ptr(bm), ptr(q), ptr(logits),
-             _dtype_code(a), N, h, w, H, W, C, nc, stream())
+             _dtype_code(a), N, h, w, H, W, C, nc, stream(),
+             work=(4 * N * h * w * C * a.element_size() + 4 * N * nc * H * W, 2 * N * h * w * C * (nc + 2)))
         ctx.save_for_backward(a, b, c, d, Wm)
         ctx.cfg = (N, C, h, w, H, W, nc, W3.shape, W3.dtype, b3.dtype)
         return logits
@@ -386,7 +404,8 @@ class _SegTail(Function):
         dW3 = torch.zeros((nc, C), device=g.device, dtype=torch.float32)
         db3 = torch.zeros(nc, device=g.device, dtype=torch.float32)
         call("ge_seg_tail_bwd", ptr(g), ptr(a), ptr(b), ptr(c), ptr(d), ptr(Wm), ptr(dq), ptr(ds), ptr(dW3),
-             ptr(db3), _dtype_code(a), N, h, w, H, W, C, nc, stream())
+             ptr(db3), _dtype_code(a), N, h, w, H, W, C, nc, stream(),
+             work=(5 * N * h * w * C * a.element_size() + 4 * N * nc * H * W, 4 * N * h * w * C * (nc + 1)))
         return ds, ds, ds, ds, dW3.view(wshape).to(wdt), db3.to(bdt), None
 
 

@@ -18,10 +18,11 @@ def contract() -> dict:
 
 
 def make_params(module: str, fill_prefix: str = "", scale: float = 1.0, key_prefix: str = "",
-                requires_grad: bool = False) -> dict:
+                requires_grad: bool = False, overrides: dict | None = None) -> dict:
     """Tensors for every state_dict entry of `module`, keyed `key_prefix + name`, filled as
     detfill would fill the reference module with prefix `fill_prefix`."""
-    spec = contract()[module]
+    spec = dict(contract()[module])
+    spec.update(overrides or {})
     out = {}
     for name, shape in spec.items():
         dtype = torch.long if name.endswith("num_batches_tracked") else torch.float32
