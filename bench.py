@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--hw", type=int, default=112)
     ap.add_argument("--num-classes", type=int, default=2)
-    ap.add_argument("--no-sync-bn", action="store_true")
+    ap.add_argument("--sync-bn", action="store_true",
+                    help="SyncBatchNorm on the network when N>1 (the reference's intent; eager only, no CUDA graphs)")
+    ap.add_argument("--no-graphs", action="store_true", help="run the static segments eagerly instead of as CUDA graphs")
     ap.add_argument("--fp32", action="store_true", help="fp32 convolutions instead of bf16 autocast")
     ap.add_argument("--cpu-sample-frames", type=int, default=16, help="frames per clip in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -179,8 +181,9 @@ def run_ours(a):
         raise SystemExit("bench.py (ours) needs a CUDA device: graphecho_b200 has no CPU fallback")
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
-    cfg = EngineConfig(hw=a.hw, num_classes=a.num_classes, bf16=not a.fp32, sync_bn=not a.no_sync_bn,
-                       cluster_backend="device")
+    graphs = not a.no_graphs and not (a.sync_bn and world > 1)
+    cfg = EngineConfig(hw=a.hw, num_classes=a.num_classes, bf16=not a.fp32, sync_bn=a.sync_bn,
+                       cluster_backend="device", cuda_graphs=graphs)
     eng = UDAEngine(cfg, dev, world)
     clips_h, masks_h = make_batch(cfg, a.clips, a.frames, rank=rank, world=world, pin=True)
     clips_d, masks_d = clips_h.to(dev), masks_h.to(dev)
@@ -221,7 +224,7 @@ def run_ours(a):
     launches0 = _cabi.launch_count()
     with ClockSampler(local) as clk:
         ms, last = timed(step_resident, a.steps)
-    launches = (_cabi.launch_count() - launches0) // max(a.steps, 1)
+    launches = (_cabi.launch_count() - launches0) // max(a.steps, 1) + eng.graph_launches
     clocks = clk.summary()
     value = world * frames_per_step / (ms / 1e3)
 
@@ -233,10 +236,26 @@ def run_ours(a):
         e2e = {"value": world * frames_per_step / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": clips_h.numel() * 4 + masks_h.numel() * 4, "d2h_bytes_per_step": 4}
 
-    # per-kernel timing of the custom kernels (CUDA events on the launching stream), one extra step
+    # per-kernel timing of the custom kernels (CUDA events on the launching stream): one extra step on
+    # an eager (graph-free) twin of the engine, so that every entry point is individually visible
+    if cfg.cuda_graphs:
+        import copy
+        ecfg = copy.copy(cfg)
+        ecfg.cuda_graphs = False
+        peng = UDAEngine(ecfg, dev, world)
+    else:
+        peng = eng
+
+    def step_profile():
+        fs, ft, shape = split_streams(clips_d)
+        return peng.train_step(fs, masks_d, ft, shape)[0]
+
+    for _ in range(2 if peng is not eng else 0):
+        step_profile()
     _cabi.profile_start()
-    step_resident()
+    step_profile()
     prof = _cabi.profile_stop()
+    del peng
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -275,7 +294,7 @@ def run_ours(a):
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if a.fp32 else "bf16", "data": "synthetic",
                 "config": {"workload": workload_name(a), "global_frames_per_step": world * frames_per_step,
-                           "parallelism": f"dp{world}", "sync_bn": bool(cfg.sync_bn and world > 1),
+                           "parallelism": f"dp{world}", "sync_bn": bool(cfg.sync_bn and world > 1), "cuda_graphs": bool(cfg.cuda_graphs),
                            "l2": "per-step working set (activations > 4 GB) exceeds the 126 MB L2; no flush needed",
                            "grad_allreduce_bytes": eng.grads.nbytes, "loss": float(last)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

@@ -41,9 +41,9 @@ _SIGNATURES = {
     "ge_tgcn_pool_concat_bwd": (c_int, [P, P, I, L, I, I, I, I, I, I, P]),
     "ge_upsample_add_fwd": (c_int, [P, P, P, I, I, I, I, I, I, I, P]),
     "ge_upsample_bwd": (c_int, [P, P, I, I, I, I, I, I, I, P]),
-    "ge_chan_stats": (c_int, [P, P, P, I, I, I, I, F, P]),
+    "ge_group_stats": (c_int, [P, P, P, I, I, I, I, I, F, P]),
     "ge_gn_relu_upsample_fwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, I, P]),
-    "ge_gn_relu_upsample_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "ge_gn_relu_upsample_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P]),
     "ge_seg_tail_fwd": (c_int, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P]),
     "ge_seg_tail_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P]),
 }

@@ -198,8 +198,7 @@ extern "C" int ge_affinity_pairwise_fwd(const float* A, const float* B, const fl
     const size_t smem = ((size_t)(TI + TJ) * (H + 4) + H) * sizeof(float);
     const size_t red = (size_t)FWD_WARPS * TI * RED_LD * sizeof(float);
     const size_t bytes = smem > red ? smem : red;
-    GE_CUDA(cudaFuncSetAttribute(affinity_pairwise_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
-            "ge_affinity_pairwise_fwd(attr)");
+    { static size_t ge_max_smem__ = 0; if ((size_t)(bytes) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(affinity_pairwise_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)), "ge_affinity_pairwise_fwd(attr)"); ge_max_smem__ = (size_t)(bytes); } }
     dim3 grid(ge::cdiv(N2, TJ), ge::cdiv(N1, TI), batch);
     affinity_pairwise_fwd_kernel<<<grid, FWD_THREADS, bytes, (cudaStream_t)stream>>>(A, B, w2, b2, M, N1, N2, H);
     GE_CHECK_LAUNCH("ge_affinity_pairwise_fwd");
@@ -228,16 +227,14 @@ extern "C" int ge_affinity_pairwise_bwd(const float* A, const float* B, const fl
     const int threads = H >= 512 ? 512 : ((H + 31) / 32) * 32;
     {
         const size_t smem = (size_t)RT * N2 * sizeof(float);
-        GE_CUDA(cudaFuncSetAttribute(affinity_pairwise_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                "ge_affinity_pairwise_bwd(attr)");
+        { static size_t ge_max_smem__ = 0; if ((size_t)(smem) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(affinity_pairwise_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)), "ge_affinity_pairwise_bwd(attr)"); ge_max_smem__ = (size_t)(smem); } }
         dim3 grid(ge::cdiv(N1, RT), batch);
         affinity_pairwise_bwd_kernel<false><<<grid, threads, smem, st>>>(A, B, w2, dM, dA, part, N1, N2, H, N1, N2);
         GE_CHECK_LAUNCH("ge_affinity_pairwise_bwd(dA)");
     }
     {
         const size_t smem = (size_t)RT * N1 * sizeof(float);
-        GE_CUDA(cudaFuncSetAttribute(affinity_pairwise_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                "ge_affinity_pairwise_bwd(attr)");
+        { static size_t ge_max_smem__ = 0; if ((size_t)(smem) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(affinity_pairwise_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)), "ge_affinity_pairwise_bwd(attr)"); ge_max_smem__ = (size_t)(smem); } }
         dim3 grid(ge::cdiv(N2, RT), batch);
         affinity_pairwise_bwd_kernel<true><<<grid, threads, smem, st>>>(B, A, w2, dM, dB, nullptr, N2, N1, H, N1, N2);
         GE_CHECK_LAUNCH("ge_affinity_pairwise_bwd(dB)");

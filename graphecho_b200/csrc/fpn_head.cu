@@ -10,6 +10,7 @@
 // All kernels are HBM-bound streaming passes: 128-bit accesses along the contiguous channel
 // axis, fp32 math, fp32 or bf16 storage.  Backward kernels are gather-form (deterministic).
 #include "common.cuh"
+#include "bilinear.cuh"
 #include <algorithm>
 #include "../../include/graphecho_b200.h"
 
@@ -17,34 +18,7 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 
-// align_corners=True source coordinate (PyTorch area_pixel_compute_scale / source index)
-__device__ __forceinline__ void src_coord(int dst, float scale, int in, int& i0, int& i1, float& l1) {
-    const float s = scale * (float)dst;
-    i0 = (int)s;
-    if (i0 > in - 1) i0 = in - 1;
-    i1 = i0 + ((i0 < in - 1) ? 1 : 0);
-    l1 = s - (float)i0;
-}
-__host__ __device__ __forceinline__ float ac_scale(int in, int out) {
-    return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
-}
-// range of destination indices whose taps can touch source index s
-__device__ __forceinline__ void dst_range(int s, float scale, int out, int& lo, int& hi) {
-    if (scale <= 0.f) { lo = 0; hi = out - 1; return; }
-    lo = (int)floorf((float)(s - 1) / scale) - 1;
-    hi = (int)ceilf((float)(s + 1) / scale) + 1;
-    if (lo < 0) lo = 0;
-    if (hi > out - 1) hi = out - 1;
-}
-// weight of destination index d onto source index s along one axis
-__device__ __forceinline__ float tap_weight(int d, int s, float scale, int in) {
-    int i0, i1; float l1;
-    src_coord(d, scale, in, i0, i1, l1);
-    float w = 0.f;
-    if (i0 == s) w += 1.f - l1;
-    if (i1 == s) w += l1;
-    return w;
-}
+using namespace ge;  // bilinear.cuh helpers
 
 // ---------------------------------------------------------------- (i) upsample + add
 template <typename T>
@@ -117,195 +91,6 @@ upsample_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dtop,
     }
     ge::Vec4<T> o; o.set(acc);
     o.store(dtop + (((size_t)n * h + sy) * w + sx) * C + cc);
-}
-
-// ---------------------------------------------------------------- (ii) per-(n,c) stats
-// CTA = (n, 32-channel block); 32 channel lanes x 8 pixel lanes.  Shifted one-pass moments.
-template <typename T>
-__global__ void __launch_bounds__(256)
-chan_stats_kernel(const T* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd,
-                  int HW, int C, float eps) {
-    __shared__ float s1[8][33], s2[8][33];
-    const int n = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), py = threadIdx.x >> 5;
-    const bool ok = c < C;
-    const T* xb = x + (size_t)n * HW * C + (ok ? c : 0);
-    const float shift = ge::to_f<T>(xb[0]);
-    float a = 0.f, b = 0.f;
-    if (ok)
-        for (int p = py; p < HW; p += 8) {
-            const float v = ge::to_f<T>(xb[(size_t)p * C]) - shift;
-            a += v;
-            b = fmaf(v, v, b);
-        }
-    s1[py][threadIdx.x & 31] = a;
-    s2[py][threadIdx.x & 31] = b;
-    __syncthreads();
-    if (py == 0 && ok) {
-        float sa = 0.f, sb = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { sa += s1[q][threadIdx.x]; sb += s2[q][threadIdx.x]; }
-        const float inv = 1.f / (float)HW;
-        const float m = sa * inv;
-        const float var = fmaxf(sb * inv - m * m, 0.f);
-        mean[(size_t)n * C + c] = m + shift;
-        rstd[(size_t)n * C + c] = 1.f / sqrtf(var + eps);
-    }
-}
-
-// out = bilinear_up( relu( (x-mean)*rstd*gamma + beta ) )
-template <typename T>
-__global__ void __launch_bounds__(256)
-gn_relu_upsample_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean,
-                            const float* __restrict__ rstd, const float* __restrict__ gamma,
-                            const float* __restrict__ beta, T* __restrict__ out,
-                            int N, int h, int w, int H, int W, int C, long long total4) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total4) return;
-    const int c4 = C >> 2;
-    const int cc = (int)(e % c4) * 4;
-    long long p = e / c4;
-    const int ox = (int)(p % W); p /= W;
-    const int oy = (int)(p % H);
-    const int n = (int)(p / H);
-    // folded affine, as PyTorch's GroupNorm kernels do: y = x*(rstd*gamma) + (beta - mean*rstd*gamma)
-    float sc[4], sh[4];
-    {
-        const float4 m = *reinterpret_cast<const float4*>(mean + (size_t)n * C + cc);
-        const float4 r = *reinterpret_cast<const float4*>(rstd + (size_t)n * C + cc);
-        const float4 g = *reinterpret_cast<const float4*>(gamma + cc);
-        const float4 bt = *reinterpret_cast<const float4*>(beta + cc);
-        const float mm[4] = {m.x, m.y, m.z, m.w}, rr[4] = {r.x, r.y, r.z, r.w};
-        const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { sc[q] = rr[q] * gg[q]; sh[q] = bb[q] - mm[q] * sc[q]; }
-    }
-    const T* xb = x + (size_t)n * h * w * C + cc;
-    float res[4];
-    if (h == H && w == W) {   // same-size _upsample is an exact identity (scale == 1, l1 == 0)
-        ge::Vec4<T> v; v.load(xb + ((size_t)oy * w + ox) * C);
-        float f[4]; v.get(f);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) res[q] = fmaxf(fmaf(f[q], sc[q], sh[q]), 0.f);
-    } else {
-        int y0, y1, x0, x1; float ly, lx;
-        src_coord(oy, ac_scale(h, H), h, y0, y1, ly);
-        src_coord(ox, ac_scale(w, W), w, x0, x1, lx);
-        const float hy = 1.f - ly, hx = 1.f - lx;
-        ge::Vec4<T> v00, v01, v10, v11;
-        v00.load(xb + ((size_t)y0 * w + x0) * C);
-        v01.load(xb + ((size_t)y0 * w + x1) * C);
-        v10.load(xb + ((size_t)y1 * w + x0) * C);
-        v11.load(xb + ((size_t)y1 * w + x1) * C);
-        float a[4], b[4], c[4], d[4];
-        v00.get(a); v01.get(b); v10.get(c); v11.get(d);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float na = fmaxf(fmaf(a[q], sc[q], sh[q]), 0.f);
-            const float nb = fmaxf(fmaf(b[q], sc[q], sh[q]), 0.f);
-            const float nc = fmaxf(fmaf(c[q], sc[q], sh[q]), 0.f);
-            const float nd = fmaxf(fmaf(d[q], sc[q], sh[q]), 0.f);
-            res[q] = hy * (hx * na + lx * nb) + ly * (hx * nc + lx * nd);
-        }
-    }
-    ge::Vec4<T> o; o.set(res);
-    o.store(out + (((size_t)n * H + oy) * W + ox) * C + cc);
-}
-
-// Backward phase 1: dyh = relu'(yhat) * upsample^T(dout) at source resolution (fp32 temp) and
-// the per-(n,c) sums S1 = sum dyh, S2 = sum dyh*xhat.  CTA = (n, 32-channel block).
-template <typename T>
-__global__ void __launch_bounds__(256)
-gn_relu_upsample_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ x,
-                                   const float* __restrict__ mean, const float* __restrict__ rstd,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ dyh, float* __restrict__ S1, float* __restrict__ S2,
-                                   int h, int w, int H, int W, int C) {
-    __shared__ float s1[8][33], s2[8][33];
-    const int n = blockIdx.y, cl = threadIdx.x & 31, c = blockIdx.x * 32 + cl, py = threadIdx.x >> 5;
-    const bool ok = c < C;
-    float a1 = 0.f, a2 = 0.f;
-    if (ok) {
-        const float m = mean[(size_t)n * C + c], r = rstd[(size_t)n * C + c];
-        const float g = gamma[c], bt = beta[c];
-        const T* xb = x + (size_t)n * h * w * C + c;
-        const T* db = dout + (size_t)n * H * W * C + c;
-        float* tb = dyh + (size_t)n * h * w * C + c;
-        const bool ident = (h == H && w == W);
-        const float scy = ac_scale(h, H), scx = ac_scale(w, W);
-        for (int p = py; p < h * w; p += 8) {
-            const int sy = p / w, sx = p - sy * w;
-            float gsum;
-            if (ident) {
-                gsum = ge::to_f<T>(db[(size_t)p * C]);
-            } else {
-                int ylo, yhi, xlo, xhi;
-                dst_range(sy, scy, H, ylo, yhi);
-                dst_range(sx, scx, W, xlo, xhi);
-                gsum = 0.f;
-                for (int oy = ylo; oy <= yhi; ++oy) {
-                    const float wy = tap_weight(oy, sy, scy, h);
-                    if (wy == 0.f) continue;
-                    for (int ox = xlo; ox <= xhi; ++ox) {
-                        const float wx = tap_weight(ox, sx, scx, w);
-                        if (wx == 0.f) continue;
-                        gsum = fmaf(wy * wx, ge::to_f<T>(db[((size_t)oy * W + ox) * C]), gsum);
-                    }
-                }
-            }
-            const float xv = ge::to_f<T>(xb[(size_t)p * C]);
-            const float xh = (xv - m) * r;
-            const float yh = fmaf(xv, r * g, bt - m * (r * g));
-            const float d = (yh > 0.f) ? gsum : 0.f;
-            tb[(size_t)p * C] = d;
-            a1 += d;
-            a2 = fmaf(d, xh, a2);
-        }
-    }
-    s1[py][cl] = a1;
-    s2[py][cl] = a2;
-    __syncthreads();
-    if (py == 0 && ok) {
-        float sa = 0.f, sb = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { sa += s1[q][cl]; sb += s2[q][cl]; }
-        S1[(size_t)n * C + c] = sa;
-        S2[(size_t)n * C + c] = sb;
-    }
-}
-
-// Backward phase 2: dx = rstd*gamma*(dyh - S1/P - xhat*S2/P)
-template <typename T>
-__global__ void __launch_bounds__(256)
-gn_bwd_apply_kernel(const float* __restrict__ dyh, const T* __restrict__ x,
-                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ gamma, const float* __restrict__ S1,
-                    const float* __restrict__ S2, T* __restrict__ dx, int HW, int C, long long total4) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total4) return;
-    const int c4 = C >> 2;
-    const int cc = (int)(e % c4) * 4;
-    const long long p = e / c4;          // n*HW + pixel
-    const int n = (int)(p / HW);
-    const float4 m = *reinterpret_cast<const float4*>(mean + (size_t)n * C + cc);
-    const float4 r = *reinterpret_cast<const float4*>(rstd + (size_t)n * C + cc);
-    const float4 g = *reinterpret_cast<const float4*>(gamma + cc);
-    const float4 a = *reinterpret_cast<const float4*>(S1 + (size_t)n * C + cc);
-    const float4 b = *reinterpret_cast<const float4*>(S2 + (size_t)n * C + cc);
-    const float4 d = *reinterpret_cast<const float4*>(dyh + (size_t)p * C + cc);
-    ge::Vec4<T> xv; xv.load(x + (size_t)p * C + cc);
-    float xf[4]; xv.get(xf);
-    const float mm[4] = {m.x, m.y, m.z, m.w}, rr[4] = {r.x, r.y, r.z, r.w}, gg[4] = {g.x, g.y, g.z, g.w};
-    const float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w}, dd[4] = {d.x, d.y, d.z, d.w};
-    const float inv = 1.f / (float)HW;
-    float res[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float xh = (xf[q] - mm[q]) * rr[q];
-        const float dxh = dd[q] * gg[q];
-        res[q] = rr[q] * (dxh - gg[q] * aa[q] * inv - xh * gg[q] * bb[q] * inv);
-    }
-    ge::Vec4<T> o; o.set(res);
-    o.store(dx + (size_t)p * C + cc);
 }
 
 // ---------------------------------------------------------------- (iii) segmentation tail
@@ -508,66 +293,6 @@ extern "C" int ge_upsample_bwd(const void* dout, void* dtop, int dtype,
                   (const bf16*)dout, (bf16*)dtop, N, h, w, H, W, C, total4);
               GE_CHECK_LAUNCH("ge_upsample_bwd"); return GE_OK; },
         "ge_upsample_bwd");
-}
-
-extern "C" int ge_chan_stats(const void* x, float* mean, float* rstd, int dtype,
-                             int N, int HW, int C, float eps, ge_stream_t stream) {
-    GE_REQUIRE(x && mean && rstd, GE_ERR_ARG, "ge_chan_stats: null pointer");
-    GE_REQUIRE(N > 0 && HW > 0 && C > 0, GE_ERR_ARG, "ge_chan_stats: bad dimension");
-    cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(ge::cdiv(C, 32), N);
-    return dispatch(dtype,
-        [&] { chan_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)x, mean, rstd, HW, C, eps);
-              GE_CHECK_LAUNCH("ge_chan_stats"); return GE_OK; },
-        [&] { chan_stats_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, mean, rstd, HW, C, eps);
-              GE_CHECK_LAUNCH("ge_chan_stats"); return GE_OK; },
-        "ge_chan_stats");
-}
-
-extern "C" int ge_gn_relu_upsample_fwd(const void* x, const float* mean, const float* rstd,
-                                       const float* gamma, const float* beta, void* out, int dtype,
-                                       int N, int h, int w, int H, int W, int C, ge_stream_t stream) {
-    GE_REQUIRE(x && mean && rstd && gamma && beta && out, GE_ERR_ARG, "ge_gn_relu_upsample_fwd: null pointer");
-    GE_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0, GE_ERR_ARG, "ge_gn_relu_upsample_fwd: bad dimension");
-    GE_REQUIRE(C % 4 == 0, GE_ERR_SHAPE, "ge_gn_relu_upsample_fwd: C=%d must be a multiple of 4", C);
-    const long long total4 = (long long)N * H * W * (C / 4);
-    cudaStream_t st = (cudaStream_t)stream;
-    return dispatch(dtype,
-        [&] { gn_relu_upsample_fwd_kernel<float><<<blocks_for(total4, 256), 256, 0, st>>>(
-                  (const float*)x, mean, rstd, gamma, beta, (float*)out, N, h, w, H, W, C, total4);
-              GE_CHECK_LAUNCH("ge_gn_relu_upsample_fwd"); return GE_OK; },
-        [&] { gn_relu_upsample_fwd_kernel<bf16><<<blocks_for(total4, 256), 256, 0, st>>>(
-                  (const bf16*)x, mean, rstd, gamma, beta, (bf16*)out, N, h, w, H, W, C, total4);
-              GE_CHECK_LAUNCH("ge_gn_relu_upsample_fwd"); return GE_OK; },
-        "ge_gn_relu_upsample_fwd");
-}
-
-// dyh: fp32 scratch [N,h,w,C]; S1,S2: fp32 [N,C] (outputs: dbeta = S1.sum(0), dgamma = S2.sum(0)).
-extern "C" int ge_gn_relu_upsample_bwd(const void* dout, const void* x, const float* mean, const float* rstd,
-                                       const float* gamma, const float* beta, float* dyh, float* S1, float* S2,
-                                       void* dx, int dtype, int N, int h, int w, int H, int W, int C,
-                                       ge_stream_t stream) {
-    GE_REQUIRE(dout && x && mean && rstd && gamma && beta && dyh && S1 && S2 && dx, GE_ERR_ARG,
-               "ge_gn_relu_upsample_bwd: null pointer");
-    GE_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0, GE_ERR_ARG, "ge_gn_relu_upsample_bwd: bad dimension");
-    GE_REQUIRE(C % 4 == 0, GE_ERR_SHAPE, "ge_gn_relu_upsample_bwd: C=%d must be a multiple of 4", C);
-    cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(ge::cdiv(C, 32), N);
-    const long long total4 = (long long)N * h * w * (C / 4);
-    return dispatch(dtype,
-        [&] { gn_relu_upsample_bwd_reduce_kernel<float><<<grid, 256, 0, st>>>(
-                  (const float*)dout, (const float*)x, mean, rstd, gamma, beta, dyh, S1, S2, h, w, H, W, C);
-              GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(reduce)");
-              gn_bwd_apply_kernel<float><<<blocks_for(total4, 256), 256, 0, st>>>(
-                  dyh, (const float*)x, mean, rstd, gamma, S1, S2, (float*)dx, h * w, C, total4);
-              GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(apply)"); return GE_OK; },
-        [&] { gn_relu_upsample_bwd_reduce_kernel<bf16><<<grid, 256, 0, st>>>(
-                  (const bf16*)dout, (const bf16*)x, mean, rstd, gamma, beta, dyh, S1, S2, h, w, H, W, C);
-              GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(reduce)");
-              gn_bwd_apply_kernel<bf16><<<blocks_for(total4, 256), 256, 0, st>>>(
-                  dyh, (const bf16*)x, mean, rstd, gamma, S1, S2, (bf16*)dx, h * w, C, total4);
-              GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(apply)"); return GE_OK; },
-        "ge_gn_relu_upsample_bwd");
 }
 
 // q: fp32 scratch/output [N,h,w,nc]; logits: fp32 NCHW [N,nc,H,W].

@@ -1,0 +1,373 @@
+// K7(ii) — GroupNorm + ReLU (+ bilinear up-sampling) on NHWC feature maps, forward and backward.
+//
+// One family of kernels serves both users on the hot path:
+//   * FPN semantic head: GroupNorm(C,C) [one channel per group] -> ReLU -> _upsample
+//     (/root/reference/models/fpnseg.py:354-355, 428-442)
+//   * Discriminator towers: GroupNorm(32,256) -> ReLU (fpnseg.py:455-466), where PyTorch eager under
+//     autocast up-casts to fp32, runs a contiguous-NCHW kernel and casts back: ~1.6 GB of traffic per
+//     layer at p2 against 0.3 GB here.
+// Every thread moves 8 consecutive channels (one 128-bit access in bf16); statistics are reduced per
+// sample by one CTA; the backward of a same-size call recomputes relu'(y)*dout on the fly instead of
+// staging it.  HBM-bound: forward = 2 reads + 1 write of the map, backward = 3 reads + 1 write.
+#include "common.cuh"
+#include "bilinear.cuh"
+#include "../../include/graphecho_b200.h"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+using namespace ge;
+
+constexpr int GN_THREADS = 512;
+
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) { load8<float>(p, f); }
+
+// sum over the `cpg` consecutive lanes of a warp that hold one group's channels
+__device__ __forceinline__ float group_lane_sum(float v, int cpg) {
+    for (int o = cpg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// ---- statistics: mean / rstd of every group, written expanded per channel [N,C] -----------------
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+group_stats_kernel(const T* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd,
+                   int HW, int C, float eps, int cpg) {
+    extern __shared__ __align__(16) float sm[];      // [nPL][C] sums, [nPL][C] squares, [C] shift
+    const int c8 = C >> 3, nPL = GN_THREADS / c8;
+    float* ssum = sm;
+    float* ssq = sm + (size_t)nPL * C;
+    float* sshift = ssq + (size_t)nPL * C;
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int co = tid % c8, pl = tid / c8;
+    const T* xb = x + (size_t)n * HW * C + co * 8;
+    float shift[8], a[8], b[8];
+    load8<T>(xb, shift);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = 0.f; b[u] = 0.f; }
+    if (pl < nPL) {
+#pragma unroll 4
+        for (int p = pl; p < HW; p += nPL) {
+            float v[8];
+            load8<T>(xb + (size_t)p * C, v);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float d = v[u] - shift[u];
+                a[u] += d;
+                b[u] = fmaf(d, d, b[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            ssum[pl * C + co * 8 + u] = a[u];
+            ssq[pl * C + co * 8 + u] = b[u];
+        }
+        if (pl == 0) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sshift[co * 8 + u] = shift[u];
+        }
+    }
+    __syncthreads();
+    const float inv = 1.f / (float)HW;
+    for (int c = tid; c < C; c += GN_THREADS) {      // C % 32 == 0 when cpg > 1: whole warps stay together
+        float sa = 0.f, sb = 0.f;
+        for (int q = 0; q < nPL; ++q) { sa += ssum[q * C + c]; sb += ssq[q * C + c]; }
+        const float sh = sshift[c];
+        float m, var;
+        if (cpg == 1) {
+            const float md = sa * inv;
+            var = fmaxf(sb * inv - md * md, 0.f);
+            m = md + sh;
+        } else {
+            // raw moments of this channel, then pooled over the group's channels
+            float S = fmaf((float)HW, sh, sa);
+            float Q = sb + 2.f * sh * sa + (float)HW * sh * sh;
+            S = group_lane_sum(S, cpg);
+            Q = group_lane_sum(Q, cpg);
+            const float ginv = inv / (float)cpg;
+            m = S * ginv;
+            var = fmaxf(Q * ginv - m * m, 0.f);
+        }
+        mean[(size_t)n * C + c] = m;
+        rstd[(size_t)n * C + c] = 1.f / sqrtf(var + eps);
+    }
+}
+
+// folded affine, as PyTorch's GroupNorm kernels do: y = x*(rstd*gamma) + (beta - mean*rstd*gamma)
+__device__ __forceinline__ void affine8(const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                        float (&sc)[8], float (&sh)[8]) {
+    float m[8], r[8], g[8], b[8];
+    load8f(mean, m); load8f(rstd, r); load8f(gamma, g); load8f(beta, b);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { sc[u] = r[u] * g[u]; sh[u] = b[u] - m[u] * sc[u]; }
+}
+
+// ---- forward: out = bilinear_up(relu(gn(x)))  (same size = identity) ----------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_relu_up_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ out,
+                      int h, int w, int H, int W, int C, long long total8) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total8) return;
+    const int c8 = C >> 3;
+    const int cc = (int)(e % c8) * 8;
+    long long p = e / c8;
+    const int ox = (int)(p % W); p /= W;
+    const int oy = (int)(p % H);
+    const int n = (int)(p / H);
+    float sc[8], sh[8], res[8];
+    affine8(mean + (size_t)n * C + cc, rstd + (size_t)n * C + cc, gamma + cc, beta + cc, sc, sh);
+    const T* xb = x + (size_t)n * h * w * C + cc;
+    if (h == H && w == W) {
+        float v[8];
+        load8<T>(xb + ((size_t)oy * w + ox) * C, v);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) res[u] = fmaxf(fmaf(v[u], sc[u], sh[u]), 0.f);
+    } else {
+        int y0, y1, x0, x1; float ly, lx;
+        src_coord(oy, ac_scale(h, H), h, y0, y1, ly);
+        src_coord(ox, ac_scale(w, W), w, x0, x1, lx);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        float a[8], b[8], c[8], d[8];
+        load8<T>(xb + ((size_t)y0 * w + x0) * C, a);
+        load8<T>(xb + ((size_t)y0 * w + x1) * C, b);
+        load8<T>(xb + ((size_t)y1 * w + x0) * C, c);
+        load8<T>(xb + ((size_t)y1 * w + x1) * C, d);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float na = fmaxf(fmaf(a[u], sc[u], sh[u]), 0.f), nb = fmaxf(fmaf(b[u], sc[u], sh[u]), 0.f);
+            const float nc = fmaxf(fmaf(c[u], sc[u], sh[u]), 0.f), nd = fmaxf(fmaf(d[u], sc[u], sh[u]), 0.f);
+            res[u] = hy * (hx * na + lx * nb) + ly * (hx * nc + lx * nd);
+        }
+    }
+    store8<T>(out + (((size_t)n * H + oy) * W + ox) * C + cc, res);
+}
+
+// gradient arriving at source pixel (sy,sx): identity or the adjoint of the bilinear gather
+template <typename T>
+__device__ __forceinline__ void upstream8(const T* db, int sy, int sx, int h, int w, int H, int W, int C,
+                                          float scy, float scx, float (&g)[8]) {
+    if (h == H && w == W) {
+        load8<T>(db + ((size_t)sy * W + sx) * C, g);
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) g[u] = 0.f;
+    int ylo, yhi, xlo, xhi;
+    dst_range(sy, scy, H, ylo, yhi);
+    dst_range(sx, scx, W, xlo, xhi);
+    for (int oy = ylo; oy <= yhi; ++oy) {
+        const float wy = tap_weight(oy, sy, scy, h);
+        if (wy == 0.f) continue;
+        for (int ox = xlo; ox <= xhi; ++ox) {
+            const float wx = tap_weight(ox, sx, scx, w);
+            if (wx == 0.f) continue;
+            float v[8];
+            load8<T>(db + ((size_t)oy * W + ox) * C, v);
+            const float ww = wy * wx;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) g[u] = fmaf(ww, v[u], g[u]);
+        }
+    }
+}
+
+// ---- backward phase 1: per-sample sums S1 = sum dyh, S2 = sum dyh*xhat, and the group terms -------
+// dyh = relu'(y) * upstream.  For an up-sampling call dyh is staged (fp32) for phase 2; for a
+// same-size call phase 2 recomputes it.
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_relu_up_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ x,
+                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                             float* __restrict__ dyh, float* __restrict__ S1, float* __restrict__ S2,
+                             float* __restrict__ A1, float* __restrict__ A2,
+                             int h, int w, int H, int W, int C, int cpg) {
+    extern __shared__ __align__(16) float sm[];
+    const int c8 = C >> 3, nPL = GN_THREADS / c8, hw = h * w;
+    float* s1 = sm;
+    float* s2 = sm + (size_t)nPL * C;
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int co = tid % c8, pl = tid / c8, cc = co * 8;
+    float a1[8], a2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a1[u] = 0.f; a2[u] = 0.f; }
+    if (pl < nPL) {
+        float sc[8], sh[8], m[8], r[8];
+        affine8(mean + (size_t)n * C + cc, rstd + (size_t)n * C + cc, gamma + cc, beta + cc, sc, sh);
+        load8f(mean + (size_t)n * C + cc, m);
+        load8f(rstd + (size_t)n * C + cc, r);
+        const T* xb = x + (size_t)n * hw * C + cc;
+        const T* db = dout + (size_t)n * H * W * C + cc;
+        const bool ident = (h == H && w == W);
+        const float scy = ac_scale(h, H), scx = ac_scale(w, W);
+        for (int p = pl; p < hw; p += nPL) {
+            const int sy = p / w, sx = p - sy * w;
+            float g[8], xv[8], d[8];
+            upstream8<T>(db, sy, sx, h, w, H, W, C, scy, scx, g);
+            load8<T>(xb + (size_t)p * C, xv);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float yh = fmaf(xv[u], sc[u], sh[u]);
+                d[u] = (yh > 0.f) ? g[u] : 0.f;
+                a1[u] += d[u];
+                a2[u] = fmaf(d[u], (xv[u] - m[u]) * r[u], a2[u]);
+            }
+            if (!ident) store8<float>(dyh + ((size_t)n * hw + p) * C + cc, d);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s1[pl * C + cc + u] = a1[u]; s2[pl * C + cc + u] = a2[u]; }
+    }
+    __syncthreads();
+    const float inv = 1.f / ((float)hw * (float)cpg);
+    for (int c = tid; c < C; c += GN_THREADS) {
+        float sa = 0.f, sb = 0.f;
+        for (int q = 0; q < nPL; ++q) { sa += s1[q * C + c]; sb += s2[q * C + c]; }
+        S1[(size_t)n * C + c] = sa;
+        S2[(size_t)n * C + c] = sb;
+        const float gm = gamma[c];
+        float ga = gm * sa, gb = gm * sb;
+        if (cpg > 1) { ga = group_lane_sum(ga, cpg); gb = group_lane_sum(gb, cpg); }
+        A1[(size_t)n * C + c] = ga * inv;
+        A2[(size_t)n * C + c] = gb * inv;
+    }
+}
+
+// ---- backward phase 2: dx = rstd * (gamma*dyh - A1 - xhat*A2) ------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_relu_up_bwd_apply_kernel(const T* __restrict__ dout, const float* __restrict__ dyh, const T* __restrict__ x,
+                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            const float* __restrict__ A1, const float* __restrict__ A2, T* __restrict__ dx,
+                            int hw, int C, int ident, long long total8) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total8) return;
+    const int c8 = C >> 3;
+    const int cc = (int)(e % c8) * 8;
+    const long long p = e / c8;              // n*hw + pixel
+    const int n = (int)(p / hw);
+    float sc[8], sh[8], m[8], r[8], g[8], a1[8], a2[8], xv[8], d[8], res[8];
+    affine8(mean + (size_t)n * C + cc, rstd + (size_t)n * C + cc, gamma + cc, beta + cc, sc, sh);
+    load8f(mean + (size_t)n * C + cc, m);
+    load8f(rstd + (size_t)n * C + cc, r);
+    load8f(gamma + cc, g);
+    load8f(A1 + (size_t)n * C + cc, a1);
+    load8f(A2 + (size_t)n * C + cc, a2);
+    load8<T>(x + (size_t)p * C + cc, xv);
+    if (ident) {
+        float up[8];
+        load8<T>(dout + (size_t)p * C + cc, up);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = (fmaf(xv[u], sc[u], sh[u]) > 0.f) ? up[u] : 0.f;
+    } else {
+        load8f(dyh + (size_t)p * C + cc, d);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float xh = (xv[u] - m[u]) * r[u];
+        res[u] = r[u] * (g[u] * d[u] - a1[u] - xh * a2[u]);
+    }
+    store8<T>(dx + (size_t)p * C + cc, res);
+}
+
+bool gn_shape_ok(int C, int cpg) {
+    if (C % 8 != 0 || C / 8 > GN_THREADS || GN_THREADS % (C / 8) != 0) return false;
+    if (cpg < 1 || C % cpg != 0) return false;
+    if (cpg > 1 && (C % 32 != 0 || cpg > 32 || (cpg & (cpg - 1)) != 0)) return false;
+    return true;
+}
+
+size_t gn_smem(int C) { return ((size_t)2 * (GN_THREADS / (C / 8)) * C + C) * sizeof(float); }
+
+template <typename K>
+int set_smem_once(K kernel, size_t bytes, size_t& cached, const char* name) {
+    if (bytes > cached) {
+        GE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), name);
+        cached = bytes;
+    }
+    return GE_OK;
+}
+
+}  // namespace
+
+// mean, rstd: fp32 [N,C], the statistics of each group written for every one of its channels.
+extern "C" int ge_group_stats(const void* x, float* mean, float* rstd, int dtype,
+                              int N, int HW, int C, int channels_per_group, float eps, ge_stream_t stream) {
+    GE_REQUIRE(x && mean && rstd, GE_ERR_ARG, "ge_group_stats: null pointer");
+    GE_REQUIRE(N > 0 && HW > 0 && C > 0, GE_ERR_ARG, "ge_group_stats: bad dimension");
+    GE_REQUIRE(gn_shape_ok(C, channels_per_group), GE_ERR_SHAPE,
+               "ge_group_stats: unsupported C=%d / channels_per_group=%d (C%%8==0, C/8 | 512, group size a power of two <= 32)",
+               C, channels_per_group);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = gn_smem(C);
+    static size_t c0 = 0, c1 = 0;
+    if (dtype == GE_DTYPE_F32) {
+        int rc = set_smem_once(group_stats_kernel<float>, smem, c0, "ge_group_stats(attr)");
+        if (rc) return rc;
+        group_stats_kernel<float><<<N, GN_THREADS, smem, st>>>((const float*)x, mean, rstd, HW, C, eps, channels_per_group);
+    } else if (dtype == GE_DTYPE_BF16) {
+        int rc = set_smem_once(group_stats_kernel<bf16>, smem, c1, "ge_group_stats(attr)");
+        if (rc) return rc;
+        group_stats_kernel<bf16><<<N, GN_THREADS, smem, st>>>((const bf16*)x, mean, rstd, HW, C, eps, channels_per_group);
+    } else { ge_set_error("ge_group_stats: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
+    GE_CHECK_LAUNCH("ge_group_stats");
+    return GE_OK;
+}
+
+extern "C" int ge_gn_relu_upsample_fwd(const void* x, const float* mean, const float* rstd,
+                                       const float* gamma, const float* beta, void* out, int dtype,
+                                       int N, int h, int w, int H, int W, int C, ge_stream_t stream) {
+    GE_REQUIRE(x && mean && rstd && gamma && beta && out, GE_ERR_ARG, "ge_gn_relu_upsample_fwd: null pointer");
+    GE_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0, GE_ERR_ARG, "ge_gn_relu_upsample_fwd: bad dimension");
+    GE_REQUIRE(C % 8 == 0, GE_ERR_SHAPE, "ge_gn_relu_upsample_fwd: C=%d must be a multiple of 8", C);
+    const long long total8 = (long long)N * H * W * (C / 8);
+    const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GE_DTYPE_F32)
+        gn_relu_up_fwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, mean, rstd, gamma, beta, (float*)out, h, w, H, W, C, total8);
+    else if (dtype == GE_DTYPE_BF16)
+        gn_relu_up_fwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)x, mean, rstd, gamma, beta, (bf16*)out, h, w, H, W, C, total8);
+    else { ge_set_error("ge_gn_relu_upsample_fwd: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
+    GE_CHECK_LAUNCH("ge_gn_relu_upsample_fwd");
+    return GE_OK;
+}
+
+// dyh: fp32 scratch [N,h,w,C], only touched when (h,w) != (H,W) (may be NULL for a same-size call);
+// S1,S2 [N,C]: dbeta = sum_n S1, dgamma = sum_n S2;  A1,A2 [N,C]: scratch.
+extern "C" int ge_gn_relu_upsample_bwd(const void* dout, const void* x, const float* mean, const float* rstd,
+                                       const float* gamma, const float* beta, float* dyh, float* S1, float* S2,
+                                       float* A1, float* A2, void* dx, int dtype, int N, int h, int w, int H, int W,
+                                       int C, int channels_per_group, ge_stream_t stream) {
+    GE_REQUIRE(dout && x && mean && rstd && gamma && beta && S1 && S2 && A1 && A2 && dx, GE_ERR_ARG,
+               "ge_gn_relu_upsample_bwd: null pointer");
+    GE_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0, GE_ERR_ARG, "ge_gn_relu_upsample_bwd: bad dimension");
+    GE_REQUIRE(gn_shape_ok(C, channels_per_group), GE_ERR_SHAPE,
+               "ge_gn_relu_upsample_bwd: unsupported C=%d / channels_per_group=%d", C, channels_per_group);
+    const int ident = (h == H && w == W) ? 1 : 0;
+    GE_REQUIRE(ident || dyh, GE_ERR_ARG, "ge_gn_relu_upsample_bwd: dyh scratch is required for an up-sampling call");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = gn_smem(C);
+    const long long total8 = (long long)N * h * w * (C / 8);
+    const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
+    static size_t c0 = 0, c1 = 0;
+    if (dtype == GE_DTYPE_F32) {
+        int rc = set_smem_once(gn_relu_up_bwd_reduce_kernel<float>, smem, c0, "ge_gn_relu_upsample_bwd(attr)");
+        if (rc) return rc;
+        gn_relu_up_bwd_reduce_kernel<float><<<N, GN_THREADS, smem, st>>>((const float*)dout, (const float*)x, mean, rstd,
+            gamma, beta, dyh, S1, S2, A1, A2, h, w, H, W, C, channels_per_group);
+        GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(reduce)");
+        gn_relu_up_bwd_apply_kernel<float><<<blocks, 256, 0, st>>>((const float*)dout, dyh, (const float*)x, mean, rstd,
+            gamma, beta, A1, A2, (float*)dx, h * w, C, ident, total8);
+    } else if (dtype == GE_DTYPE_BF16) {
+        int rc = set_smem_once(gn_relu_up_bwd_reduce_kernel<bf16>, smem, c1, "ge_gn_relu_upsample_bwd(attr)");
+        if (rc) return rc;
+        gn_relu_up_bwd_reduce_kernel<bf16><<<N, GN_THREADS, smem, st>>>((const bf16*)dout, (const bf16*)x, mean, rstd,
+            gamma, beta, dyh, S1, S2, A1, A2, h, w, H, W, C, channels_per_group);
+        GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(reduce)");
+        gn_relu_up_bwd_apply_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)dout, dyh, (const bf16*)x, mean, rstd,
+            gamma, beta, A1, A2, (bf16*)dx, h * w, C, ident, total8);
+    } else { ge_set_error("ge_gn_relu_upsample_bwd: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
+    GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(apply)");
+    return GE_OK;
+}

@@ -116,8 +116,7 @@ extern "C" int ge_mrconv_gather_fwd(const float* x, const float* y, const long l
     GE_REQUIRE(y != nullptr || N == M, GE_ERR_SHAPE, "ge_mrconv_gather_fwd: self-graph needs M == N");
     const size_t smem = (size_t)2 * MR_THREADS * k * sizeof(int);
     GE_REQUIRE(smem <= 200 * 1024, GE_ERR_CAPACITY, "ge_mrconv_gather_fwd: k too large");
-    GE_CUDA(cudaFuncSetAttribute(mrconv_gather_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-            "ge_mrconv_gather_fwd(attr)");
+    { static size_t ge_max_smem__ = 0; if ((size_t)(smem) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(mrconv_gather_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)), "ge_mrconv_gather_fwd(attr)"); ge_max_smem__ = (size_t)(smem); } }
     mrconv_gather_fwd_kernel<<<dim3(ge::cdiv(N, MR_THREADS), B), MR_THREADS, smem, (cudaStream_t)stream>>>(
         x, y, idx_nbr, idx_ctr, out, argk, C, N, M, k);
     GE_CHECK_LAUNCH("ge_mrconv_gather_fwd");

@@ -318,8 +318,7 @@ extern "C" int ge_sinkhorn_distance_fwd(const float* x, const float* y, float* C
     GE_REQUIRE(smem <= kCap, GE_ERR_CAPACITY,
                "ge_sinkhorn_distance_fwd: P1=%d x P2=%d does not fit one CTA's shared memory", P1, P2);
     cudaStream_t st = (cudaStream_t)stream;
-    GE_CUDA(cudaFuncSetAttribute(sd_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-            "ge_sinkhorn_distance_fwd(attr)");
+    { static size_t ge_max_smem__ = 0; if ((size_t)(smem) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(sd_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)), "ge_sinkhorn_distance_fwd(attr)"); ge_max_smem__ = (size_t)(smem); } }
     sd_iterate_kernel<<<B, SD_THREADS, smem, st>>>(x, y, C, hist_u, hist_v, err, P1, P2, D, eps, max_iter);
     GE_CHECK_LAUNCH("ge_sinkhorn_distance_fwd(iterate)");
     sd_finalize_kernel<<<B, SD_THREADS, 0, st>>>(C, hist_u, hist_v, err, pi, cost, nits, B, P1, P2, eps, max_iter, thresh);
@@ -340,13 +339,11 @@ extern "C" int ge_sinkhorn_distance_bwd(const float* x, const float* y, const fl
     GE_REQUIRE(smem <= kCap, GE_ERR_CAPACITY,
                "ge_sinkhorn_distance_bwd: P1=%d x P2=%d does not fit one CTA's shared memory", P1, P2);
     cudaStream_t st = (cudaStream_t)stream;
-    GE_CUDA(cudaFuncSetAttribute(sd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-            "ge_sinkhorn_distance_bwd(attr)");
+    { static size_t ge_max_smem__ = 0; if ((size_t)(smem) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(sd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)), "ge_sinkhorn_distance_bwd(attr)"); ge_max_smem__ = (size_t)(smem); } }
     sd_bwd_kernel<<<B, SD_THREADS, smem, st>>>(C, hist_u, hist_v, nits, gcost, dC, P1, P2, eps, max_iter);
     GE_CHECK_LAUNCH("ge_sinkhorn_distance_bwd(sweep)");
     const size_t smem2 = (size_t)P1 * P2 * sizeof(float);
-    GE_CUDA(cudaFuncSetAttribute(sd_bwd_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2),
-            "ge_sinkhorn_distance_bwd(attr2)");
+    { static size_t ge_max_smem__ = 0; if ((size_t)(smem2) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(sd_bwd_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem2)), "ge_sinkhorn_distance_bwd(attr2)"); ge_max_smem__ = (size_t)(smem2); } }
     dim3 grid(ge::cdiv(D, 256), B);
     sd_bwd_xy_kernel<<<grid, 256, smem2, st>>>(x, y, dC, dx, dy, P1, P2, D);
     GE_CHECK_LAUNCH("ge_sinkhorn_distance_bwd(xy)");

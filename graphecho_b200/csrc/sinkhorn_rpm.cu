@@ -368,8 +368,18 @@ int pick_cluster(int N1, int N2, bool bwd, int requested) {
 
 template <typename K, typename... Args>
 int launch_cluster(K kernel, const char* name, int cs, int batch, size_t smem, cudaStream_t st, Args... args) {
-    GE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
-    if (cs > 8) GE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), name);
+    // attributes are set once per process and kernel (template instantiation), so that a stream
+    // capture only ever sees the launch itself
+    static size_t max_smem_set = 0;
+    static bool nonportable_set = false;
+    if (smem > max_smem_set) {
+        GE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        max_smem_set = smem;
+    }
+    if (cs > 8 && !nonportable_set) {
+        GE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), name);
+        nonportable_set = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(cs * batch));
     cfg.blockDim = dim3(RPM_THREADS);

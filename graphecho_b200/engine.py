@@ -48,6 +48,7 @@ class EngineConfig:
     lr_aux: float = 2.5e-3
     weight_decay: float = 1e-4
     cluster_backend: str = "device"     # GModule.update_seed bipartition: 'device' | 'sklearn'
+    cuda_graphs: bool = False           # capture the static segments (FPN, Grapher, discriminators) as CUDA graphs
     seed: int = 0
 
 
@@ -155,6 +156,8 @@ class UDAEngine:
         for m in modules:
             m.train()
         self.grads = FlatGradSync(modules)
+        self.graphed = False
+        self.graph_launches = 0      # graphecho_b200 kernels replayed per step inside the CUDA graphs
         self.opt = {"Net": torch.optim.Adam(self.network.parameters(), lr=cfg.lr_net, betas=(0.9, 0.999),
                                             weight_decay=cfg.weight_decay, fused=device.type == "cuda")}
         for name, m in self.aux.items():
@@ -162,6 +165,49 @@ class UDAEngine:
                                              weight_decay=cfg.weight_decay, fused=device.type == "cuda")
 
     # ------------------------------------------------------------------------------------------
+    def capture_graphs(self, n_frames: int):
+        """Capture the shape-static segments of the step -- the segmentation network, the p2 Grapher and
+        the four discriminators, forward and backward -- as CUDA graphs (torch.cuda.make_graphed_callables),
+        so that ~3 500 of the step's ~4 000 kernel launches are replayed by a dozen graph launches.  The
+        data-dependent part (GModule: node sampling, matching) stays eager.  `n_frames` = source + target
+        frames per step on this rank (the segments are re-captured if it changes)."""
+        cfg, dev = self.cfg, self.device
+        if self.world > 1 and cfg.sync_bn:
+            raise RuntimeError("cuda_graphs with SyncBatchNorm is not supported: use sync_bn=False")
+        ns = n_frames // 2
+        x = torch.zeros(n_frames, 1, cfg.hw, cfg.hw, device=dev)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16):
+            _, feats = self.network(x)
+        calls, samples, names = [self.network], [(x,)], ["network"]
+        if cfg.graph_matching and cfg.vig_grapher:
+            calls.append(self.aux["Grapher"])
+            samples.append((torch.zeros_like(feats[0]).requires_grad_(),))
+            names.append("Grapher")
+        if cfg.graph_matching and cfg.discriminator:
+            for i, lvl in enumerate(("P2", "P3", "P4", "P5")):
+                f = feats[i]
+                calls.append(self.aux[f"Dis_{lvl}"])
+                samples.append(((torch.zeros_like(f[:ns]).requires_grad_(), torch.zeros_like(f[ns:]).requires_grad_()),))
+                names.append(f"Dis_{lvl}")
+        del feats
+        from . import _cabi
+        before = _cabi.launch_count()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16, cache_enabled=False):
+            graphed = torch.cuda.make_graphed_callables(tuple(calls), tuple(samples), num_warmup_iters=3)
+        # 3 warm-up executions + 1 capture of every segment's forward and backward
+        self.graph_launches = (_cabi.launch_count() - before) // 4
+        for name, g in zip(names, graphed):
+            if name == "network":
+                self.network = g
+            else:
+                self.aux[name] = g
+        self.grads.zero()
+        self.graphed = True
+        self._graph_frames = n_frames
+
+    def _autocast(self):
+        return torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.cfg.bf16, cache_enabled=not self.graphed)
+
     def seg_loss(self, logits, masks):
         return self.dice(logits, masks) + F.binary_cross_entropy_with_logits(logits, masks)
 
@@ -170,21 +216,23 @@ class UDAEngine:
         cfg = self.cfg
         ns = frames_src.shape[0]
         losses = {}
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16):
+        if cfg.cuda_graphs and not self.graphed:
+            self.capture_graphs(frames_src.shape[0] + frames_tgt.shape[0])
+        with self._autocast():
             logits, feats = self.network(torch.cat([frames_src, frames_tgt], dim=0))
         pred_s, pred_t = logits[:ns], logits[ns:]
         losses["seg_loss"] = cfg.seg_weight * self.seg_loss(pred_s, masks_src)
         if not cfg.graph_matching:
             return losses
         if cfg.vig_grapher:
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16):
+            with self._autocast():
                 feats = [self.aux["Grapher"](feats[0])] + list(feats[1:])
         fs, ft = [f[:ns] for f in feats], [f[ns:] for f in feats]
         score_maps = torch.where(torch.sigmoid(pred_t) > 0.5, 1, 0)                # train_cardiac_uda.py:235
         (fs, ft), nodes, mid = self.aux["Graph"](None, (fs, ft), targets=masks_src, score_maps=score_maps)
         losses.update(mid)
         if cfg.discriminator:
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16):
+            with self._autocast():
                 for i, lvl in enumerate(("p2", "p3", "p4", "p5")):
                     losses[f"loss_adv_{lvl}"] = 0.1 * self.aux[f"Dis_{lvl.upper()}"]((fs[i], ft[i]))
         if cfg.temporal_graph and clips_shape is not None and nodes[0].numel() > 0 and nodes[0].dim() == 2:

@@ -333,44 +333,53 @@ def upsample_bilinear(x, size):
 
 class _GnReluUpsample(Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, size, eps):
+    def forward(ctx, x, gamma, beta, size, eps, groups):
         _need_cuda(x, gamma, beta)
         xc = _nhwc_view(x)
         N, C, h, w = xc.shape
         H, W = size
+        cpg = C // groups
         g, b = _f32c(gamma), _f32c(beta)
         mean = torch.empty((N, C), device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         code = _dtype_code(xc)
         es = xc.element_size()
-        call("ge_chan_stats", ptr(xc), ptr(mean), ptr(rstd), code, N, h * w, C, c_float(eps), stream(),
+        call("ge_group_stats", ptr(xc), ptr(mean), ptr(rstd), code, N, h * w, C, cpg, c_float(eps), stream(),
              work=(N * C * h * w * es, 3 * N * C * h * w))
         out = torch.empty((N, C, H, W), device=x.device, dtype=xc.dtype, memory_format=torch.channels_last)
         call("ge_gn_relu_upsample_fwd", ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(out), code,
              N, h, w, H, W, C, stream(), work=(N * C * es * (h * w + H * W), 12 * N * C * H * W))
         ctx.save_for_backward(xc, mean, rstd, g, b)
-        ctx.cfg = (N, C, h, w, H, W, gamma.dtype, beta.dtype)
+        ctx.cfg = (N, C, h, w, H, W, cpg, gamma.dtype, beta.dtype)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         xc, mean, rstd, g, b = ctx.saved_tensors
-        N, C, h, w, H, W, gdt, bdt = ctx.cfg
+        N, C, h, w, H, W, cpg, gdt, bdt = ctx.cfg
         d = _nhwc_view(dout.to(xc.dtype))
-        dyh = torch.empty((N, h, w, C), device=d.device, dtype=torch.float32)
-        S1 = torch.empty((N, C), device=d.device, dtype=torch.float32)
-        S2 = torch.empty_like(S1)
+        ident = (h, w) == (H, W)
+        dyh = None if ident else torch.empty((N, h, w, C), device=d.device, dtype=torch.float32)
+        S = torch.empty((4, N, C), device=d.device, dtype=torch.float32)
         dx = torch.empty_like(xc)
+        es = xc.element_size()
         call("ge_gn_relu_upsample_bwd", ptr(d), ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dyh),
-             ptr(S1), ptr(S2), ptr(dx), _dtype_code(xc), N, h, w, H, W, C, stream(),
-             work=(N * C * (xc.element_size() * (H * W + 3 * h * w) + 8 * h * w), 20 * N * C * H * W))
-        return dx, S2.sum(0).to(gdt), S1.sum(0).to(bdt), None, None
+             ptr(S[0]), ptr(S[1]), ptr(S[2]), ptr(S[3]), ptr(dx), _dtype_code(xc), N, h, w, H, W, C, cpg, stream(),
+             work=(N * C * (es * (H * W + 3 * h * w) + (0 if ident else 8 * h * w)), 20 * N * C * H * W))
+        return dx, S[1].sum(0).to(gdt), S[0].sum(0).to(bdt), None, None, None
 
 
-def gn_relu_upsample(x, gamma, beta, size, eps=1e-5):
-    """_upsample(relu(GroupNorm(C,C)(x)), size) with align_corners=True (fpnseg.py:428-442)."""
-    return _GnReluUpsample.apply(x, gamma, beta, (int(size[0]), int(size[1])), float(eps))
+def gn_relu_upsample(x, gamma, beta, size, eps=1e-5, groups=None):
+    """_upsample(relu(GroupNorm(groups, C)(x)), size), align_corners=True; groups=None means one
+    channel per group (the FPN head's GroupNorm(C,C), fpnseg.py:428-442)."""
+    groups = x.shape[1] if groups is None else int(groups)
+    return _GnReluUpsample.apply(x, gamma, beta, (int(size[0]), int(size[1])), float(eps), groups)
+
+
+def gn_relu(x, gamma, beta, groups, eps=1e-5):
+    """relu(GroupNorm(groups, C)(x)) on an NHWC map (Discriminator towers, fpnseg.py:455-466)."""
+    return _GnReluUpsample.apply(x, gamma, beta, (int(x.shape[2]), int(x.shape[3])), float(eps), int(groups))
 
 
 class _SegTail(Function):

@@ -224,15 +224,24 @@ class Discriminator(nn.Module):
         self.grl_applied_domain = grl_applied_domain
         self.source_label, self.target_label = 1.0, 0.0
 
+    def _tower(self, x):
+        """conv3x3 -> fused GroupNorm(32)+ReLU (one NHWC pass, no fp32 up-cast) per tower stage."""
+        x = x.contiguous(memory_format=torch.channels_last)
+        mods = list(self.dis_tower)
+        for i in range(0, len(mods), 3):
+            conv, gn = mods[i], mods[i + 1]
+            x = GF.gn_relu(conv(x), gn.weight, gn.bias, gn.num_groups, gn.eps)
+        return self.cls_logits(x).float()
+
     def forward(self, feature, domain="source"):
         fs, ft = feature
         _need_cuda(fs)
         ns = fs.shape[0]
         if fs.shape[1:] == ft.shape[1:]:
-            x = self.cls_logits(self.dis_tower(self.grad_reverse(torch.cat([fs, ft], dim=0)))).float()
+            x = self._tower(self.grad_reverse(torch.cat([fs, ft], dim=0)))
             xs, xt = x[:ns], x[ns:]
         else:
-            xs = self.cls_logits(self.dis_tower(self.grad_reverse(fs))).float()
-            xt = self.cls_logits(self.dis_tower(self.grad_reverse(ft))).float()
+            xs = self._tower(self.grad_reverse(fs))
+            xt = self._tower(self.grad_reverse(ft))
         return self.loss_fn(xs, torch.full_like(xs, self.source_label)) + \
             self.loss_fn(xt, torch.full_like(xt, self.target_label))

@@ -127,17 +127,21 @@ int ge_upsample_add_fwd(const void* top, const void* lateral, void* out, int dty
 /* adjoint of the up-sampling: dtop [N,h,w,C] from dout [N,H,W,C] (d lateral = dout). */
 int ge_upsample_bwd(const void* dout, void* dtop, int dtype,
                     int N, int h, int w, int H, int W, int C, ge_stream_t stream);
-/* (ii) GroupNorm(C,C)+ReLU+_upsample (fpnseg.py:428-442).  Per-(n,c) mean / rstd over HW: */
-int ge_chan_stats(const void* x, float* mean, float* rstd, int dtype,
-                  int N, int HW, int C, float eps, ge_stream_t stream);
-/* out [N,H,W,C] = bilinear_up(relu((x-mean)*rstd*gamma+beta)); x [N,h,w,C]; (h,w)==(H,W) = identity. */
+/* (ii) GroupNorm + ReLU (+ _upsample): the semantic head's GroupNorm(C,C) (fpnseg.py:354-355, 428-442)
+ *      and the Discriminator towers' GroupNorm(32,256)+ReLU (fpnseg.py:455-466).
+ *      Group statistics over HW x channels_per_group, written per channel: mean, rstd fp32 [N,C]. */
+int ge_group_stats(const void* x, float* mean, float* rstd, int dtype,
+                   int N, int HW, int C, int channels_per_group, float eps, ge_stream_t stream);
+/* out [N,H,W,C] = bilinear_up(relu((x-mean)*rstd*gamma+beta)); x [N,h,w,C]; (h,w)==(H,W) = no up-sampling. */
 int ge_gn_relu_upsample_fwd(const void* x, const float* mean, const float* rstd,
                             const float* gamma, const float* beta, void* out, int dtype,
                             int N, int h, int w, int H, int W, int C, ge_stream_t stream);
-/* dx [N,h,w,C]; dyh fp32 scratch [N,h,w,C]; S1,S2 fp32 [N,C]: dbeta = sum_n S1, dgamma = sum_n S2. */
+/* dx [N,h,w,C]; dyh fp32 scratch [N,h,w,C] (only for an up-sampling call, else may be NULL);
+ * S1,S2 fp32 [N,C]: dbeta = sum_n S1, dgamma = sum_n S2; A1,A2 fp32 [N,C] scratch. */
 int ge_gn_relu_upsample_bwd(const void* dout, const void* x, const float* mean, const float* rstd,
                             const float* gamma, const float* beta, float* dyh, float* S1, float* S2,
-                            void* dx, int dtype, int N, int h, int w, int H, int W, int C, ge_stream_t stream);
+                            float* A1, float* A2, void* dx, int dtype, int N, int h, int w, int H, int W,
+                            int C, int channels_per_group, ge_stream_t stream);
 /* (iii) logits = bilinear_up_x4(conv3(s2+s3+s4+s5))  (fpnseg.py:444).  s* [N,h,w,C]; W3 [nc,C],
  *       b3 [nc]; q fp32 [N,h,w,nc] (conv3 output before up-sampling); logits fp32 NCHW [N,nc,H,W]. */
 int ge_seg_tail_fwd(const void* s2, const void* s3, const void* s4, const void* s5,

@@ -307,6 +307,29 @@ def test_gn_relu_upsample(dev, h, H, C):
     close(bd.grad, bo.grad, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("C,groups,h,dtype", [(256, 32, 28, torch.float32), (256, 32, 7, torch.float32),
+                                              (64, 32, 9, torch.float32), (256, 32, 14, torch.bfloat16),
+                                              (128, 128, 5, torch.bfloat16), (512, 16, 4, torch.float32)])
+def test_gn_relu_groups(dev, C, groups, h, dtype):
+    """GroupNorm(groups, C) + ReLU as the Discriminator towers use it (fpnseg.py:455-466)."""
+    torch.manual_seed(C + groups + h)
+    x = (torch.randn(3, C, h, h) * 1.3 + 0.4).to(dtype).float()
+    gamma, beta = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    xo, go, bo = x.clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    ref = torch.relu(F.group_norm(xo, groups, go, bo, 1e-5))
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    xd, gd, bd = _cl(x, dev, dtype).requires_grad_(), gamma.to(dev).requires_grad_(), beta.to(dev).requires_grad_()
+    out = GF.gn_relu(xd, gd, bd, groups)
+    assert out.dtype == dtype
+    lo = dtype == torch.bfloat16
+    close(out, ref, rtol=2e-2 if lo else 1e-4, atol=2e-2 if lo else 1e-5)
+    (out * W.to(dev).to(dtype)).sum().backward()
+    close(xd.grad, xo.grad, rtol=5e-2 if lo else 2e-3, atol=5e-2 if lo else 2e-4)
+    close(gd.grad, go.grad, rtol=3e-2 if lo else 1e-3, atol=0.3 if lo else 1e-3)
+    close(bd.grad, bo.grad, rtol=3e-2 if lo else 1e-3, atol=0.3 if lo else 1e-3)
+
+
 @pytest.mark.parametrize("nc,h", [(1, 28), (2, 28), (4, 64), (3, 16)])
 def test_seg_tail(dev, nc, h):
     torch.manual_seed(nc * 10 + h)
