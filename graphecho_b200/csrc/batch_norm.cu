@@ -1,0 +1,348 @@
+// Fused BatchNorm2d (+ residual add) (+ ReLU) on NHWC feature maps, training and inference, forward and
+// backward — the glue between the backbone's tensor-core convolutions.
+//
+// The reference runs nn.BatchNorm2d, the residual `out += identity` and nn.ReLU as separate full-tensor
+// passes (/root/reference/models/fpnseg.py:192-212 Bottleneck.forward, :251-255 stem, :27-142 VGG16
+// blocks): 8 tensor passes forward and 8 backward per residual block output.  Here:
+//   forward : partial statistics (1 read) -> finalize (+ running-stat update) -> apply (1-2 reads, 1 write)
+//   backward: partial sums of dy*relu' and dy*relu'*xhat (3 reads) -> finalize (dgamma, dbeta) ->
+//             apply (3 reads, 1-2 writes)
+// Statistics are reduced in two deterministic stages (per-CTA partials in a workspace, then one small
+// CTA), never with atomics.  Each thread moves 8 consecutive channels (one 128-bit access in bf16).
+// HBM-bound; algorithmic bytes per element (bf16): forward 6 (+2 with a residual), backward 14 (+2).
+#include "common.cuh"
+#include "../../include/graphecho_b200.h"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+using namespace ge;
+
+constexpr int BN_THREADS = 256;
+
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) { load8<float>(p, f); }
+
+// ---- stage 1 (forward): per-CTA partial sums of (x - shift) and (x - shift)^2 --------------------
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_partial_stats_kernel(const T* __restrict__ x, const float* __restrict__ shift_src, float* __restrict__ part,
+                        long long P, int C, long long pix_per_cta) {
+    extern __shared__ __align__(16) float sm[];       // [nPL][C] x 2
+    const int c8 = C >> 3, nPL = BN_THREADS / c8;
+    float* ssum = sm;
+    float* ssq = sm + (size_t)nPL * C;
+    const int tid = threadIdx.x, co = tid % c8, pl = tid / c8;
+    const long long p0 = (long long)blockIdx.x * pix_per_cta;
+    const long long p1 = min(P, p0 + pix_per_cta);
+    float shift[8], a[8], b[8];
+    load8f(shift_src + co * 8, shift);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = 0.f; b[u] = 0.f; }
+    if (pl < nPL) {
+        const T* xb = x + co * 8;
+#pragma unroll 4
+        for (long long p = p0 + pl; p < p1; p += nPL) {
+            float v[8];
+            load8<T>(xb + p * C, v);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float d = v[u] - shift[u];
+                a[u] += d;
+                b[u] = fmaf(d, d, b[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { ssum[pl * C + co * 8 + u] = a[u]; ssq[pl * C + co * 8 + u] = b[u]; }
+    }
+    __syncthreads();
+    float* out = part + (size_t)blockIdx.x * 2 * C;
+    for (int c = tid; c < C; c += BN_THREADS) {
+        float sa = 0.f, sb = 0.f;
+        for (int q = 0; q < nPL; ++q) { sa += ssum[q * C + c]; sb += ssq[q * C + c]; }
+        out[c] = sa;
+        out[C + c] = sb;
+    }
+}
+
+// ---- stage 2 (forward): batch mean / rstd, running statistics (nn.BatchNorm2d semantics) --------
+__global__ void __launch_bounds__(256)
+bn_finalize_stats_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ shift_src,
+                         float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                         long long P, int C, float eps, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float sa = 0.f, sb = 0.f;
+    for (int q = 0; q < nparts; ++q) { sa += part[(size_t)q * 2 * C + c]; sb += part[(size_t)q * 2 * C + C + c]; }
+    const float inv = 1.f / (float)P;
+    const float md = sa * inv;
+    const float var = fmaxf(sb * inv - md * md, 0.f);          // biased, used to normalise
+    const float mean = md + shift_src[c];
+    save_mean[c] = mean;
+    save_rstd[c] = 1.f / sqrtf(var + eps);
+    if (running_mean != nullptr) {
+        const float unbiased = P > 1 ? var * ((float)P / (float)(P - 1)) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+}
+
+// ---- stage 3 (forward): out = act( x*sc + sh (+ residual) ) --------------------------------------
+// MODE 0: training (sc/sh from save_mean/save_rstd); MODE 1: inference (from running stats, `rstd` = var)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+bn_apply_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ mean,
+                    const float* __restrict__ rstd_or_var, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, T* __restrict__ out, int C, float eps, int relu, long long total8) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total8) return;
+    const int c8 = C >> 3;
+    const int cc = (int)(e % c8) * 8;
+    float m[8], r[8], g[8], b[8], v[8], o[8];
+    load8f(mean + cc, m); load8f(rstd_or_var + cc, r); load8f(gamma + cc, g); load8f(beta + cc, b);
+    load8<T>(x + e * 8, v);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float rs = (MODE == 0) ? r[u] : 1.f / sqrtf(r[u] + eps);
+        const float sc = rs * g[u];
+        o[u] = fmaf(v[u], sc, b[u] - m[u] * sc);
+    }
+    if (res != nullptr) {
+        float rv[8];
+        load8<T>(res + e * 8, rv);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] += rv[u];
+    }
+    if (relu) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = fmaxf(o[u], 0.f);
+    }
+    store8<T>(out + e * 8, o);
+}
+
+// ---- backward stage 1: partial sums of dyr = dy * relu'(out) and dyr * xhat ----------------------
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_partial_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ out, const T* __restrict__ x,
+                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ part,
+                      long long P, int C, long long pix_per_cta, int relu) {
+    extern __shared__ __align__(16) float sm[];
+    const int c8 = C >> 3, nPL = BN_THREADS / c8;
+    float* s1 = sm;
+    float* s2 = sm + (size_t)nPL * C;
+    const int tid = threadIdx.x, co = tid % c8, pl = tid / c8, cc = co * 8;
+    const long long p0 = (long long)blockIdx.x * pix_per_cta;
+    const long long p1 = min(P, p0 + pix_per_cta);
+    float m[8], r[8], a[8], b[8];
+    load8f(mean + cc, m); load8f(rstd + cc, r);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = 0.f; b[u] = 0.f; }
+    if (pl < nPL) {
+#pragma unroll 2
+        for (long long p = p0 + pl; p < p1; p += nPL) {
+            float g[8], xv[8];
+            load8<T>(dy + p * C + cc, g);
+            load8<T>(x + p * C + cc, xv);
+            if (relu) {
+                float ov[8];
+                load8<T>(out + p * C + cc, ov);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) g[u] = (ov[u] > 0.f) ? g[u] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a[u] += g[u];
+                b[u] = fmaf(g[u], (xv[u] - m[u]) * r[u], b[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s1[pl * C + cc + u] = a[u]; s2[pl * C + cc + u] = b[u]; }
+    }
+    __syncthreads();
+    float* o = part + (size_t)blockIdx.x * 2 * C;
+    for (int c = tid; c < C; c += BN_THREADS) {
+        float sa = 0.f, sb = 0.f;
+        for (int q = 0; q < nPL; ++q) { sa += s1[q * C + c]; sb += s2[q * C + c]; }
+        o[c] = sa;
+        o[C + c] = sb;
+    }
+}
+
+// ---- backward stage 2: dbeta = S1, dgamma = S2 ----------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_finalize_bwd_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float sa = 0.f, sb = 0.f;
+    for (int q = 0; q < nparts; ++q) { sa += part[(size_t)q * 2 * C + c]; sb += part[(size_t)q * 2 * C + C + c]; }
+    dbeta[c] = sa;
+    dgamma[c] = sb;
+}
+
+// ---- backward stage 3: dx = rstd*gamma*(dyr - S1/P - xhat*S2/P)   [training]
+//                        dx = dyr * gamma / sqrt(var+eps)            [inference];  dres = dyr ----------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+bn_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ out, const T* __restrict__ x,
+                    const float* __restrict__ mean, const float* __restrict__ rstd_or_var,
+                    const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                    const float* __restrict__ dbeta, T* __restrict__ dx, T* __restrict__ dres,
+                    int C, float eps, float invP, int relu, long long total8) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total8) return;
+    const int c8 = C >> 3;
+    const int cc = (int)(e % c8) * 8;
+    float m[8], r[8], g[8], gv[8], o[8];
+    load8f(mean + cc, m); load8f(rstd_or_var + cc, r); load8f(gamma + cc, g);
+    load8<T>(dy + e * 8, gv);
+    if (relu) {
+        float ov[8];
+        load8<T>(out + e * 8, ov);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) gv[u] = (ov[u] > 0.f) ? gv[u] : 0.f;
+    }
+    if (dres != nullptr) store8<T>(dres + e * 8, gv);
+    if (MODE == 0) {
+        float s1[8], s2[8], xv[8];
+        load8f(dbeta + cc, s1); load8f(dgamma + cc, s2);
+        load8<T>(x + e * 8, xv);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float xh = (xv[u] - m[u]) * r[u];
+            o[u] = r[u] * g[u] * (gv[u] - s1[u] * invP - xh * s2[u] * invP);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = gv[u] * g[u] / sqrtf(r[u] + eps);
+    }
+    store8<T>(dx + e * 8, o);
+}
+
+int bn_chunks(long long P, int C) {
+    const int nPL = BN_THREADS / (C / 8);
+    long long want = P / ((long long)nPL * 8);           // >= 8 pixels per pixel-lane
+    const long long cap = (long long)ge::sm_count() * 4;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+bool bn_shape_ok(int C) { return C % 8 == 0 && C / 8 <= BN_THREADS && BN_THREADS % (C / 8) == 0; }
+
+size_t bn_smem(int C) { return (size_t)2 * (BN_THREADS / (C / 8)) * C * sizeof(float); }
+
+}  // namespace
+
+extern "C" size_t ge_bn_workspace_bytes(long long P, int C) {
+    if (P <= 0 || C <= 0 || !bn_shape_ok(C)) return 0;
+    return (size_t)bn_chunks(P, C) * 2 * C * sizeof(float);
+}
+
+// x, residual (or NULL), out: [P,C] NHWC-flattened (P = N*H*W) in `dtype`; gamma, beta, running_*,
+// save_mean, save_rstd: fp32 [C].  running_* may be NULL (track_running_stats=False).
+extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps,
+                               void* out, float* save_mean, float* save_rstd, void* workspace, size_t workspace_bytes,
+                               int dtype, long long P, int C, int relu, ge_stream_t stream) {
+    GE_REQUIRE(x && gamma && beta && out && save_mean && save_rstd && workspace, GE_ERR_ARG, "ge_bn_fwd_train: null pointer");
+    GE_REQUIRE(P > 0 && C > 0, GE_ERR_ARG, "ge_bn_fwd_train: bad dimension");
+    GE_REQUIRE(bn_shape_ok(C), GE_ERR_SHAPE, "ge_bn_fwd_train: unsupported channel count C=%d (C%%8==0, C/8 | 256)", C);
+    GE_REQUIRE(workspace_bytes >= ge_bn_workspace_bytes(P, C), GE_ERR_ARG, "ge_bn_fwd_train: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = bn_chunks(P, C);
+    const long long ppc = ge::cdivll(P, chunks);
+    const size_t smem = bn_smem(C);
+    float* part = static_cast<float*>(workspace);
+    // shift = running mean when tracked (close to the batch mean), else beta-free zero shift via gamma-less trick
+    const float* shift = running_mean != nullptr ? running_mean : save_mean;
+    if (running_mean == nullptr) GE_CUDA(cudaMemsetAsync(save_mean, 0, (size_t)C * sizeof(float), st), "ge_bn_fwd_train(memset)");
+    const long long total8 = P * (C / 8);
+    const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
+    static size_t c0 = 0, c1 = 0;
+    if (dtype == GE_DTYPE_F32) {
+        if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(bn_partial_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_fwd_train(attr)"); c0 = smem; }
+        bn_partial_stats_kernel<float><<<chunks, BN_THREADS, smem, st>>>((const float*)x, shift, part, P, C, ppc);
+    } else if (dtype == GE_DTYPE_BF16) {
+        if (smem > c1) { GE_CUDA(cudaFuncSetAttribute(bn_partial_stats_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_fwd_train(attr)"); c1 = smem; }
+        bn_partial_stats_kernel<bf16><<<chunks, BN_THREADS, smem, st>>>((const bf16*)x, shift, part, P, C, ppc);
+    } else { ge_set_error("ge_bn_fwd_train: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
+    GE_CHECK_LAUNCH("ge_bn_fwd_train(stats)");
+    bn_finalize_stats_kernel<<<ge::cdiv(C, 256), 256, 0, st>>>(part, chunks, shift, save_mean, save_rstd,
+                                                               running_mean, running_var, P, C, eps, momentum);
+    GE_CHECK_LAUNCH("ge_bn_fwd_train(finalize)");
+    if (dtype == GE_DTYPE_F32)
+        bn_apply_fwd_kernel<float, 0><<<blocks, 256, 0, st>>>((const float*)x, (const float*)residual, save_mean, save_rstd,
+                                                               gamma, beta, (float*)out, C, eps, relu, total8);
+    else
+        bn_apply_fwd_kernel<bf16, 0><<<blocks, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, save_mean, save_rstd,
+                                                              gamma, beta, (bf16*)out, C, eps, relu, total8);
+    GE_CHECK_LAUNCH("ge_bn_fwd_train(apply)");
+    return GE_OK;
+}
+
+extern "C" int ge_bn_fwd_eval(const void* x, const void* residual, const float* gamma, const float* beta,
+                              const float* running_mean, const float* running_var, float eps, void* out,
+                              int dtype, long long P, int C, int relu, ge_stream_t stream) {
+    GE_REQUIRE(x && gamma && beta && running_mean && running_var && out, GE_ERR_ARG, "ge_bn_fwd_eval: null pointer");
+    GE_REQUIRE(P > 0 && C > 0, GE_ERR_ARG, "ge_bn_fwd_eval: bad dimension");
+    GE_REQUIRE(C % 8 == 0, GE_ERR_SHAPE, "ge_bn_fwd_eval: C=%d must be a multiple of 8", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total8 = P * (C / 8);
+    const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
+    if (dtype == GE_DTYPE_F32)
+        bn_apply_fwd_kernel<float, 1><<<blocks, 256, 0, st>>>((const float*)x, (const float*)residual, running_mean, running_var,
+                                                               gamma, beta, (float*)out, C, eps, relu, total8);
+    else if (dtype == GE_DTYPE_BF16)
+        bn_apply_fwd_kernel<bf16, 1><<<blocks, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, running_mean, running_var,
+                                                              gamma, beta, (bf16*)out, C, eps, relu, total8);
+    else { ge_set_error("ge_bn_fwd_eval: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
+    GE_CHECK_LAUNCH("ge_bn_fwd_eval");
+    return GE_OK;
+}
+
+// Training-mode backward: mean / rstd = save_mean / save_rstd of the forward.  dres (or NULL) receives the
+// gradient of the residual input.  dgamma, dbeta fp32 [C] (overwritten).
+extern "C" int ge_bn_bwd(const void* dy, const void* out, const void* x, const float* gamma,
+                         const float* mean, const float* rstd_or_var, float eps, void* dx, void* dres,
+                         float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                         int dtype, long long P, int C, int relu, ge_stream_t stream) {
+    GE_REQUIRE(dy && x && gamma && mean && rstd_or_var && dx && dgamma && dbeta && workspace, GE_ERR_ARG, "ge_bn_bwd: null pointer");
+    GE_REQUIRE(!relu || out, GE_ERR_ARG, "ge_bn_bwd: the forward output is needed for the ReLU mask");
+    GE_REQUIRE(P > 0 && C > 0, GE_ERR_ARG, "ge_bn_bwd: bad dimension");
+    GE_REQUIRE(bn_shape_ok(C), GE_ERR_SHAPE, "ge_bn_bwd: unsupported channel count C=%d", C);
+    GE_REQUIRE(workspace_bytes >= ge_bn_workspace_bytes(P, C), GE_ERR_ARG, "ge_bn_bwd: workspace too small");
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_bwd: unsupported dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = bn_chunks(P, C);
+    const long long ppc = ge::cdivll(P, chunks);
+    const size_t smem = bn_smem(C);
+    float* part = static_cast<float*>(workspace);
+    const long long total8 = P * (C / 8);
+    const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
+    static size_t c0 = 0, c1 = 0;
+    const float* rstd = rstd_or_var;
+    if (dtype == GE_DTYPE_F32) {
+        if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(bn_partial_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_bwd(attr)"); c0 = smem; }
+    } else {
+        if (smem > c1) { GE_CUDA(cudaFuncSetAttribute(bn_partial_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_bwd(attr)"); c1 = smem; }
+    }
+    if (dtype == GE_DTYPE_F32)
+        bn_partial_bwd_kernel<float><<<chunks, BN_THREADS, smem, st>>>((const float*)dy, (const float*)out, (const float*)x,
+                                                                       mean, rstd, part, P, C, ppc, relu);
+    else
+        bn_partial_bwd_kernel<bf16><<<chunks, BN_THREADS, smem, st>>>((const bf16*)dy, (const bf16*)out, (const bf16*)x,
+                                                                      mean, rstd, part, P, C, ppc, relu);
+    GE_CHECK_LAUNCH("ge_bn_bwd(partial)");
+    bn_finalize_bwd_kernel<<<ge::cdiv(C, 256), 256, 0, st>>>(part, chunks, dgamma, dbeta, C);
+    GE_CHECK_LAUNCH("ge_bn_bwd(finalize)");
+    const float invP = 1.f / (float)P;
+    if (dtype == GE_DTYPE_F32)
+        bn_apply_bwd_kernel<float, 0><<<blocks, 256, 0, st>>>((const float*)dy, (const float*)out, (const float*)x, mean, rstd,
+            gamma, dgamma, dbeta, (float*)dx, (float*)dres, C, eps, invP, relu, total8);
+    else
+        bn_apply_bwd_kernel<bf16, 0><<<blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)out, (const bf16*)x, mean, rstd,
+            gamma, dgamma, dbeta, (bf16*)dx, (bf16*)dres, C, eps, invP, relu, total8);
+    GE_CHECK_LAUNCH("ge_bn_bwd(apply)");
+    return GE_OK;
+}

@@ -382,6 +382,83 @@ def gn_relu(x, gamma, beta, groups, eps=1e-5):
     return _GnReluUpsample.apply(x, gamma, beta, (int(x.shape[2]), int(x.shape[3])), float(eps), int(groups))
 
 
+class _BnAct(Function):
+    """Training-mode fused BatchNorm2d (+ residual) (+ ReLU) on an NHWC map."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, momentum, eps, relu):
+        _need_cuda(x, residual, gamma, beta)
+        xc = _nhwc_view(x)
+        N, C, H, W = xc.shape
+        P = N * H * W
+        rc = _nhwc_view(residual.to(xc.dtype)) if residual is not None else None
+        g, b = _f32c(gamma), _f32c(beta)
+        dev = x.device
+        out = torch.empty_like(xc)
+        save = torch.empty((2, C), device=dev, dtype=torch.float32)
+        nbytes = _cabi.lib().ge_bn_workspace_bytes(P, C)
+        if nbytes == 0:
+            raise _cabi.GraphEchoNativeError(f"fused BatchNorm does not support C={C}")
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        es = xc.element_size()
+        call("ge_bn_fwd_train", ptr(xc), ptr(rc), ptr(g), ptr(b), ptr(running_mean), ptr(running_var),
+             c_float(momentum), c_float(eps), ptr(out), ptr(save[0]), ptr(save[1]), ptr(ws), c_size_t(nbytes),
+             _dtype_code(xc), c_longlong(P), C, int(relu), stream(),
+             work=(P * C * es * (3 + (1 if rc is not None else 0)), 8 * P * C))
+        ctx.save_for_backward(xc, out, g, save)
+        ctx.cfg = (P, C, float(eps), bool(relu), rc is not None, gamma.dtype, beta.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        xc, out, g, save = ctx.saved_tensors
+        P, C, eps, relu, has_res, gdt, bdt = ctx.cfg
+        d = _nhwc_view(dout.to(xc.dtype))
+        dx = torch.empty_like(xc)
+        dres = torch.empty_like(xc) if has_res else None
+        dgb = torch.empty((2, C), device=d.device, dtype=torch.float32)
+        nbytes = _cabi.lib().ge_bn_workspace_bytes(P, C)
+        ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        es = xc.element_size()
+        call("ge_bn_bwd", ptr(d), ptr(out), ptr(xc), ptr(g), ptr(save[0]), ptr(save[1]), c_float(eps), ptr(dx),
+             ptr(dres), ptr(dgb[0]), ptr(dgb[1]), ptr(ws), c_size_t(nbytes), _dtype_code(xc), c_longlong(P), C,
+             int(relu), stream(), work=(P * C * es * (7 + (1 if has_res else 0)), 16 * P * C))
+        return dx, dres, dgb[0].to(gdt), dgb[1].to(bdt), None, None, None, None, None
+
+
+def bn_act(x, bn, residual=None, relu=True):
+    """relu(BatchNorm2d(x) + residual) with `bn` an nn.BatchNorm2d (parameters / buffers are read and,
+    in training mode, updated exactly as the module would).  Other norm types (e.g. SyncBatchNorm)
+    fall back to the module itself."""
+    if type(bn) is not torch.nn.BatchNorm2d or not bn.affine or (bn.training and bn.momentum is None):
+        y = bn(x)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if relu else y
+    if bn.training or not bn.track_running_stats:
+        rm = bn.running_mean if bn.track_running_stats else None
+        rv = bn.running_var if bn.track_running_stats else None
+        if bn.track_running_stats:
+            bn.num_batches_tracked.add_(1)
+        return _BnAct.apply(x, residual, bn.weight, bn.bias, rm, rv, float(bn.momentum), float(bn.eps), bool(relu))
+    # inference: a per-channel affine map -- differentiable through ordinary autograd if anyone asks
+    if torch.is_grad_enabled() and (x.requires_grad or bn.weight.requires_grad):
+        y = torch.nn.functional.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if relu else y
+    xc = _nhwc_view(x)
+    N, C, H, W = xc.shape
+    rc = _nhwc_view(residual.to(xc.dtype)) if residual is not None else None
+    out = torch.empty_like(xc)
+    es = xc.element_size()
+    call("ge_bn_fwd_eval", ptr(xc), ptr(rc), ptr(_f32c(bn.weight)), ptr(_f32c(bn.bias)), ptr(bn.running_mean),
+         ptr(bn.running_var), c_float(bn.eps), ptr(out), _dtype_code(xc), c_longlong(N * H * W), C, int(relu), stream(),
+         work=(N * H * W * C * es * (2 + (1 if rc is not None else 0)), 4 * N * H * W * C))
+    return out
+
+
 class _SegTail(Function):
     @staticmethod
     def forward(ctx, s2, s3, s4, s5, W3, b3, scale):

@@ -49,7 +49,10 @@ class VGG16(nn.Module):
     def forward(self, x):
         feats = []
         for b in range(1, 6):
-            x = getattr(self, f"block_{b}")(x)
+            mods = list(getattr(self, f"block_{b}"))
+            for i in range(0, len(mods) - 1, 3):          # (conv, BN, ReLU) triples -> conv + fused BN+ReLU
+                x = GF.bn_act(mods[i](x), mods[i + 1], relu=True)
+            x = mods[-1](x)                                # max-pool
             feats.append(x)
         return feats
 
@@ -70,11 +73,10 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        identity = x if self.downsample is None else self.downsample(x)
-        return self.relu(out + identity)
+        out = GF.bn_act(self.conv1(x), self.bn1, relu=True)
+        out = GF.bn_act(self.conv2(out), self.bn2, relu=True)
+        identity = x if self.downsample is None else GF.bn_act(self.downsample[0](x), self.downsample[1], relu=False)
+        return GF.bn_act(self.conv3(out), self.bn3, residual=identity, relu=True)   # BN + add + ReLU in one pass
 
 
 class ResNet(nn.Module):
@@ -115,7 +117,7 @@ class ResNet(nn.Module):
                 m.bias.data.zero_()
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(GF.bn_act(self.conv1(x), self.bn1, relu=True))
         feats = [x]
         for stage in (self.layer1, self.layer2, self.layer3, self.layer4):
             x = stage(x)

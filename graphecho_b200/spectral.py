@@ -18,10 +18,21 @@ import torch
 
 
 @torch.no_grad()
-def spectral_bipartition(pts: torch.Tensor, n_neighbors: int) -> torch.Tensor:
+def spectral_bipartition(pts: torch.Tensor, n_neighbors: int, iterations: int = 300) -> torch.Tensor:
     """pts [n, d] (row 0 = the class seed).  Returns bool [n-1]: True where a point lands in the same
-    cluster as row 0."""
+    cluster as row 0.  CUDA inputs up to ge_spectral_bipartition_max_points() run as ONE kernel
+    (csrc/spectral.cu: power iteration instead of a full eigendecomposition); larger or CPU inputs take
+    the dense torch.linalg.eigh route below (same algorithm)."""
     n = pts.shape[0]
+    if pts.is_cuda:
+        from . import _cabi
+        if n <= _cabi.lib().ge_spectral_bipartition_max_points():
+            x = pts.float().contiguous()
+            keep = torch.empty(n - 1, device=pts.device, dtype=torch.uint8)
+            _cabi.call("ge_spectral_bipartition", _cabi.ptr(x), _cabi.ptr(keep), n, x.shape[1],
+                       max(1, min(int(n_neighbors), n)), int(iterations), _cabi.stream(),
+                       work=(4 * n * x.shape[1] + n, 2 * n * n * (x.shape[1] + n + iterations)))
+            return keep.bool()
     x = pts.float()
     k = max(1, min(int(n_neighbors), n))
     sq = (x * x).sum(1)

@@ -152,6 +152,35 @@ int ge_seg_tail_bwd(const float* dlogits, const void* s2, const void* s3, const 
                     const float* W3, float* dq, void* ds, float* dW3, float* db3, int dtype,
                     int N, int h, int w, int H, int W, int C, int nc, ge_stream_t stream);
 
+/* ---- fused BatchNorm2d (+ residual add) (+ ReLU) on NHWC maps ---------------------------------
+ * nn.BatchNorm2d + `out += identity` + nn.ReLU of Bottleneck.forward / the ResNet stem / the VGG16
+ * blocks (models/fpnseg.py:192-212, 251-255, 27-142).  x, residual (or NULL), out: [P,C] with
+ * P = N*H*W, in `dtype`; gamma, beta, running_*, save_* fp32 [C].  Training mode uses batch statistics
+ * (biased variance), updates running_* with `momentum` (unbiased variance) exactly as nn.BatchNorm2d,
+ * and saves mean / rstd for the backward.  Two-stage deterministic reductions through `workspace`. */
+size_t ge_bn_workspace_bytes(long long P, int C);
+int ge_bn_fwd_train(const void* x, const void* residual, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps,
+                    void* out, float* save_mean, float* save_rstd, void* workspace, size_t workspace_bytes,
+                    int dtype, long long P, int C, int relu, ge_stream_t stream);
+int ge_bn_fwd_eval(const void* x, const void* residual, const float* gamma, const float* beta,
+                   const float* running_mean, const float* running_var, float eps, void* out,
+                   int dtype, long long P, int C, int relu, ge_stream_t stream);
+/* dx [P,C]; dres [P,C] or NULL (gradient of the residual input); dgamma, dbeta fp32 [C]. */
+int ge_bn_bwd(const void* dy, const void* out, const void* x, const float* gamma,
+              const float* mean, const float* rstd, float eps, void* dx, void* dres,
+              float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+              int dtype, long long P, int C, int relu, ge_stream_t stream);
+
+/* ---- update_seed: spectral bipartition ------------------------------------------------------
+ * What GModule.update_seed asks sklearn's SpectralClustering(2, affinity='nearest_neighbors',
+ * n_neighbors, assign_labels='kmeans') for (models/graph_matching.py:532-567), on the device:
+ * pts fp32 [n,d] with row 0 = the class seed; keep uint8 [n-1] = 1 where point i+1 lands in the
+ * seed's cluster.  One CTA, n <= ge_spectral_bipartition_max_points(). */
+int ge_spectral_bipartition_max_points(void);
+int ge_spectral_bipartition(const float* pts, unsigned char* keep, int n, int d, int n_neighbors,
+                            int iterations, ge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

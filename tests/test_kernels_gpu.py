@@ -350,3 +350,72 @@ def test_seg_tail(dev, nc, h):
         close(a.grad, b.grad, rtol=1e-3, atol=1e-4)
     close(Wd.grad, Wo.grad, rtol=1e-3, atol=1e-2)
     close(bd.grad, bo.grad, rtol=1e-3, atol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------- update_seed
+def test_spectral_bipartition_kernel_matches_dense_route(dev):
+    """The one-CTA power-iteration kernel against the dense eigh route of graphecho_b200/spectral.py
+    (itself checked against sklearn on CPU in test_host_logic.py)."""
+    from graphecho_b200.spectral import spectral_bipartition
+    agree = []
+    for seed in range(10):
+        g = torch.Generator().manual_seed(seed)
+        n = int(torch.randint(25, 150, (1,), generator=g))
+        a = torch.randn(n, 256, generator=g)
+        a[: n // 3] += 1.5 * torch.randn(1, 256, generator=g)          # two blobs, as LayerNorm'd class nodes
+        pts = torch.cat([torch.randn(1, 256, generator=g), a])
+        ref = spectral_bipartition(pts, n // 2)                         # CPU: dense route
+        out = spectral_bipartition(pts.to(dev), n // 2).cpu()
+        agree.append((out == ref).float().mean().item())
+    assert min(agree) > 0.97, agree
+
+
+# ---------------------------------------------------------------------------------------- fused BatchNorm
+@pytest.mark.parametrize("C,hw,res,relu,dtype", [(64, 28, False, True, torch.float32), (256, 14, True, True, torch.float32),
+                                                 (2048, 4, True, True, torch.float32), (512, 7, False, False, torch.float32),
+                                                 (1024, 7, True, True, torch.bfloat16), (128, 56, False, True, torch.bfloat16)])
+def test_bn_act_train_and_eval(dev, C, hw, res, relu, dtype):
+    """Fused BN(+residual)(+ReLU) against nn.BatchNorm2d + add + relu (fp32 oracle on CPU): output,
+    grads of x / residual / gamma / beta, running statistics, then inference mode."""
+    torch.manual_seed(C + hw)
+    N = 5
+    x = (torch.randn(N, C, hw, hw) * 1.4 + 0.3).to(dtype).float()
+    r = torch.randn(N, C, hw, hw).to(dtype).float() if res else None
+    ref_bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        ref_bn.weight.copy_(1 + 0.1 * torch.randn(C)); ref_bn.bias.copy_(0.1 * torch.randn(C))
+        ref_bn.running_mean.copy_(0.05 * torch.randn(C)); ref_bn.running_var.copy_(1 + 0.1 * torch.rand(C))
+    import copy
+    our_bn = copy.deepcopy(ref_bn).to(dev)
+    xo = x.clone().requires_grad_()
+    ro = r.clone().requires_grad_() if res else None
+    y = ref_bn(xo)
+    if res:
+        y = y + ro
+    ref = torch.relu(y) if relu else y
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    xd = _cl(x, dev, dtype).requires_grad_()
+    rd = _cl(r, dev, dtype).requires_grad_() if res else None
+    out = GF.bn_act(xd, our_bn, residual=rd, relu=relu)
+    assert out.dtype == dtype
+    lo = dtype == torch.bfloat16
+    close(out, ref, rtol=2e-2 if lo else 1e-4, atol=3e-2 if lo else 2e-5)
+    (out * W.to(dev).to(dtype)).sum().backward()
+    close(xd.grad, xo.grad, rtol=5e-2 if lo else 2e-3, atol=5e-2 if lo else 2e-4)
+    if res:
+        close(rd.grad, ro.grad, rtol=2e-2 if lo else 1e-5, atol=2e-2 if lo else 1e-6)
+    scale = float(ref_bn.weight.grad.abs().max())
+    close(our_bn.weight.grad, ref_bn.weight.grad, rtol=3e-2 if lo else 1e-3, atol=(3e-2 if lo else 1e-4) * scale)
+    close(our_bn.bias.grad, ref_bn.bias.grad, rtol=3e-2 if lo else 1e-3, atol=(3e-2 if lo else 1e-4) * scale)
+    close(our_bn.running_mean, ref_bn.running_mean, rtol=1e-4, atol=1e-5)
+    close(our_bn.running_var, ref_bn.running_var, rtol=1e-4, atol=1e-5)
+    assert int(our_bn.num_batches_tracked) == 1
+    ref_bn.eval(); our_bn.eval()
+    with torch.no_grad():
+        y = ref_bn(x)
+        if res:
+            y = y + r
+        ref_e = torch.relu(y) if relu else y
+        out_e = GF.bn_act(_cl(x, dev, dtype), our_bn, residual=None if not res else _cl(r, dev, dtype), relu=relu)
+    close(out_e, ref_e, rtol=2e-2 if lo else 1e-4, atol=3e-2 if lo else 2e-5)
