@@ -64,16 +64,36 @@ bn_partial_stats_kernel(const T* __restrict__ x, const float* __restrict__ shift
     }
 }
 
+// Sum the per-CTA partials of 32 channels with 8 part-lanes (CTA = 256 threads, grid = ceil(C/32)).
+__device__ __forceinline__ void reduce_parts(const float* __restrict__ part, int nparts, int C, int c, int lane8,
+                                             float (*sh)[2][33], float& sa, float& sb) {
+    float a = 0.f, b = 0.f;
+    if (c < C)
+        for (int q = lane8; q < nparts; q += 8) {
+            a += part[(size_t)q * 2 * C + c];
+            b += part[(size_t)q * 2 * C + C + c];
+        }
+    sh[lane8][0][threadIdx.x & 31] = a;
+    sh[lane8][1][threadIdx.x & 31] = b;
+    __syncthreads();
+    sa = 0.f; sb = 0.f;
+    if (lane8 == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { sa += sh[q][0][threadIdx.x & 31]; sb += sh[q][1][threadIdx.x & 31]; }
+    }
+}
+
 // ---- stage 2 (forward): batch mean / rstd, running statistics (nn.BatchNorm2d semantics) --------
 __global__ void __launch_bounds__(256)
 bn_finalize_stats_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ shift_src,
                          float* __restrict__ save_mean, float* __restrict__ save_rstd,
                          float* __restrict__ running_mean, float* __restrict__ running_var,
                          long long P, int C, float eps, float momentum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float sa = 0.f, sb = 0.f;
-    for (int q = 0; q < nparts; ++q) { sa += part[(size_t)q * 2 * C + c]; sb += part[(size_t)q * 2 * C + C + c]; }
+    __shared__ float sh[8][2][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane8 = threadIdx.x >> 5;
+    float sa, sb;
+    reduce_parts(part, nparts, C, c, lane8, sh, sa, sb);
+    if (lane8 != 0 || c >= C) return;
     const float inv = 1.f / (float)P;
     const float md = sa * inv;
     const float var = fmaxf(sb * inv - md * md, 0.f);          // biased, used to normalise
@@ -172,10 +192,11 @@ bn_partial_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ out, const
 __global__ void __launch_bounds__(256)
 bn_finalize_bwd_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float sa = 0.f, sb = 0.f;
-    for (int q = 0; q < nparts; ++q) { sa += part[(size_t)q * 2 * C + c]; sb += part[(size_t)q * 2 * C + C + c]; }
+    __shared__ float sh[8][2][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane8 = threadIdx.x >> 5;
+    float sa, sb;
+    reduce_parts(part, nparts, C, c, lane8, sh, sa, sb);
+    if (lane8 != 0 || c >= C) return;
     dbeta[c] = sa;
     dgamma[c] = sb;
 }
@@ -268,7 +289,7 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
         bn_partial_stats_kernel<bf16><<<chunks, BN_THREADS, smem, st>>>((const bf16*)x, shift, part, P, C, ppc);
     } else { ge_set_error("ge_bn_fwd_train: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_bn_fwd_train(stats)");
-    bn_finalize_stats_kernel<<<ge::cdiv(C, 256), 256, 0, st>>>(part, chunks, shift, save_mean, save_rstd,
+    bn_finalize_stats_kernel<<<ge::cdiv(C, 32), 256, 0, st>>>(part, chunks, shift, save_mean, save_rstd,
                                                                running_mean, running_var, P, C, eps, momentum);
     GE_CHECK_LAUNCH("ge_bn_fwd_train(finalize)");
     if (dtype == GE_DTYPE_F32)
@@ -334,7 +355,7 @@ extern "C" int ge_bn_bwd(const void* dy, const void* out, const void* x, const f
         bn_partial_bwd_kernel<bf16><<<chunks, BN_THREADS, smem, st>>>((const bf16*)dy, (const bf16*)out, (const bf16*)x,
                                                                       mean, rstd, part, P, C, ppc, relu);
     GE_CHECK_LAUNCH("ge_bn_bwd(partial)");
-    bn_finalize_bwd_kernel<<<ge::cdiv(C, 256), 256, 0, st>>>(part, chunks, dgamma, dbeta, C);
+    bn_finalize_bwd_kernel<<<ge::cdiv(C, 32), 256, 0, st>>>(part, chunks, dgamma, dbeta, C);
     GE_CHECK_LAUNCH("ge_bn_bwd(finalize)");
     const float invP = 1.f / (float)P;
     if (dtype == GE_DTYPE_F32)

@@ -24,13 +24,14 @@ constexpr int KNN_THREADS = 256;
 constexpr int XLD = TQ + 4;    // padded leading dim of the staged chunks
 constexpr int DLD = TK + 1;    // padded leading dim of the distance tile
 
-// den[b][n] = max(||x[b,:,n]||_2, 1e-12);  sq[b][n] = sum_c (x/den)^2
+// xn[b,:,n] = x[b,:,n] / max(||x[b,:,n]||_2, 1e-12)  (F.normalize, vig.py:372-373);  sq[b][n] = sum_c xn^2
 __global__ void __launch_bounds__(128)
-knn_norm_kernel(const float* __restrict__ x, float* __restrict__ den, float* __restrict__ sq, int C, int N) {
+knn_norm_kernel(const float* __restrict__ x, float* __restrict__ xn, float* __restrict__ sq, int C, int N) {
     const int b = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const float* xb = x + (size_t)b * C * N + n;
+    float* ob = xn + (size_t)b * C * N + n;
     float s = 0.f;
     for (int c = 0; c < C; ++c) {
         const float v = xb[(size_t)c * N];
@@ -40,9 +41,9 @@ knn_norm_kernel(const float* __restrict__ x, float* __restrict__ den, float* __r
     float q = 0.f;
     for (int c = 0; c < C; ++c) {
         const float v = xb[(size_t)c * N] / d;
+        ob[(size_t)c * N] = v;
         q = fmaf(v, v, q);
     }
-    den[(size_t)b * N + n] = d;
     sq[(size_t)b * N + n] = q;
 }
 
@@ -84,14 +85,13 @@ __device__ __forceinline__ float list_kth(const TopList& L, int K) {
 
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_graph_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                 const float* __restrict__ xden, const float* __restrict__ xsq,
-                 const float* __restrict__ yden, const float* __restrict__ ysq,
+                 const float* __restrict__ xsq, const float* __restrict__ ysq,
                  const float* __restrict__ rel, long long* __restrict__ out,
                  int B, int C, int N, int M, int K, int dilation) {
     __shared__ __align__(16) float Xs[KC][XLD];
     __shared__ __align__(16) float Ys[KC][XLD];
     __shared__ float Ds[TQ][DLD];
-    __shared__ float s_xden[TQ], s_xsq[TQ], s_yden[TK], s_ysq[TK];
+    __shared__ float s_xsq[TQ], s_ysq[TK];
 
     const int b = blockIdx.y, i0 = blockIdx.x * TQ;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -101,7 +101,6 @@ knn_graph_kernel(const float* __restrict__ x, const float* __restrict__ y,
 
     if (tid < TQ) {
         const int i = i0 + tid;
-        s_xden[tid] = (i < N) ? xden[(size_t)b * N + i] : 1.f;
         s_xsq[tid] = (i < N) ? xsq[(size_t)b * N + i] : 0.f;
     }
 
@@ -116,7 +115,6 @@ knn_graph_kernel(const float* __restrict__ x, const float* __restrict__ y,
         __syncthreads();  // previous tile's Ds / s_y* fully consumed
         if (tid < TK) {
             const int j = j0 + tid;
-            s_yden[tid] = (j < M) ? yden[(size_t)b * M + j] : 1.f;
             s_ysq[tid] = (j < M) ? ysq[(size_t)b * M + j] : 0.f;
         }
         float acc[4][4];
@@ -132,8 +130,8 @@ knn_graph_kernel(const float* __restrict__ x, const float* __restrict__ y,
                 const int c = c0 + kc;
                 float xv = 0.f, yv = 0.f;
                 if (c < C) {
-                    if (i0 + p < N) xv = xb[(size_t)c * N + i0 + p] / s_xden[p];
-                    if (j0 + p < M) yv = yb[(size_t)c * M + j0 + p] / s_yden[p];
+                    if (i0 + p < N) xv = xb[(size_t)c * N + i0 + p];
+                    if (j0 + p < M) yv = yb[(size_t)c * M + j0 + p];
                 }
                 Xs[kc][p] = xv;
                 Ys[kc][p] = yv;
@@ -208,12 +206,164 @@ knn_graph_kernel(const float* __restrict__ x, const float* __restrict__ y,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path (N%4 == 0, M%4 == 0, C%32 == 0, query tile fits shared memory): the 64-query tile of the
+// normalised x stays RESIDENT in shared memory for the whole CTA ([C][68] floats), key tiles stream
+// through a 2-stage cp.async ring in 32-channel chunks (16-byte copies, zero-fill past the edge), so the
+// FFMA loop never waits on a synchronous global load and nothing is divided in the loop.
+constexpr int FKC = 32;
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(gmem_src), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N_)); }
+
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_graph_fast_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                      const float* __restrict__ xsq, const float* __restrict__ ysq,
+                      const float* __restrict__ rel, long long* __restrict__ out,
+                      int B, int C, int N, int M, int K, int dilation) {
+    extern __shared__ __align__(16) float smem[];
+    float* Xr = smem;                              // [C][XLD]
+    float* Yb = Xr + (size_t)C * XLD;              // [2][FKC][XLD]
+    float* Ds = Yb + 2 * FKC * XLD;                // [TQ][DLD]
+    float* s_xsq = Ds + TQ * DLD;                  // [TQ]
+    float* s_ysq = s_xsq + TQ;                     // [TK]
+
+    const int b = blockIdx.y, i0 = blockIdx.x * TQ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    const float* xb = x + (size_t)b * C * N;
+    const float* yb = y + (size_t)b * C * M;
+    const int nchunks = C / FKC;
+    const int ntiles = (M + TK - 1) / TK;
+
+    // resident query tile
+    for (int e = tid; e < C * (TQ / 4); e += KNN_THREADS) {
+        const int c = e / (TQ / 4), p4 = (e - c * (TQ / 4)) * 4;
+        cp_async16(Xr + c * XLD + p4, xb + (size_t)c * N + i0 + p4, i0 + p4 < N);
+    }
+    cp_async_commit();
+    if (tid < TQ) s_xsq[tid] = (i0 + tid < N) ? xsq[(size_t)b * N + i0 + tid] : 0.f;
+
+    auto issue = [&](int step) {            // step = tile * nchunks + chunk
+        const int tile = step / nchunks, ch = step - tile * nchunks;
+        const int j0 = tile * TK, c0 = ch * FKC;
+        float* dst = Yb + (step & 1) * FKC * XLD;
+        for (int e = tid; e < FKC * (TK / 4); e += KNN_THREADS) {
+            const int kc = e / (TK / 4), p4 = (e - kc * (TK / 4)) * 4;
+            cp_async16(dst + kc * XLD + p4, yb + (size_t)(c0 + kc) * M + j0 + p4, j0 + p4 < M);
+        }
+        cp_async_commit();
+    };
+
+    TopList lists[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        lists[r].d0 = INFINITY; lists[r].d1 = INFINITY;
+        lists[r].i0 = 0; lists[r].i1 = 0;
+    }
+
+    const int nsteps = ntiles * nchunks;
+    issue(0);
+    float acc[4][4];
+    for (int step = 0; step < nsteps; ++step) {
+        const int tile = step / nchunks, ch = step - tile * nchunks;
+        if (ch == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+        }
+        if (step + 1 < nsteps) { issue(step + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();                       // chunk `step` (and the resident tile) visible to all
+        const float* Xc = Xr + (size_t)ch * FKC * XLD;
+        const float* Yc = Yb + (step & 1) * FKC * XLD;
+#pragma unroll
+        for (int kc = 0; kc < FKC; ++kc) {
+            const float4 a4 = *reinterpret_cast<const float4*>(Xc + kc * XLD + ty * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(Yc + kc * XLD + tx * 4);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+        }
+        if (ch == nchunks - 1) {
+            const int j0 = tile * TK;
+            if (tid < TK) s_ysq[tid] = (j0 + tid < M) ? ysq[(size_t)b * M + j0 + tid] : 0.f;
+            __syncthreads();                   // s_ysq ready; previous tile's Ds consumed
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int il = ty * 4 + a, jl = tx * 4 + c;
+                    float d = (s_xsq[il] + (-2.f * acc[a][c])) + s_ysq[jl];
+                    const int i = i0 + il, j = j0 + jl;
+                    if (rel != nullptr && i < N && j < M) d += rel[(size_t)i * M + j];
+                    if (j >= M) d = INFINITY;
+                    Ds[il * DLD + jl] = d;
+                }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int il = warp * 8 + r;
+                TopList& L = lists[r];
+                float thr = list_kth(L, K);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int jl = lane + 32 * h;
+                    const float d = Ds[il * DLD + jl];
+                    unsigned pass = __ballot_sync(ge::kFull, d < thr);
+                    while (pass) {
+                        const int src = __ffs(pass) - 1;
+                        pass &= pass - 1;
+                        const float dc = __shfl_sync(ge::kFull, d, src);
+                        if (dc < thr) {
+                            list_insert(L, dc, j0 + src + 32 * h, K, lane);
+                            thr = list_kth(L, K);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();                       // everyone done with buffer (step & 1) before it is refilled
+    }
+    const int kout = K / dilation;
+    long long* out0 = out + (size_t)b * N * kout;
+    long long* out1 = out + (size_t)B * N * kout + (size_t)b * N * kout;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = i0 + warp * 8 + r;
+        if (i >= N) continue;
+        const TopList& L = lists[r];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int sidx = lane + 32 * h;
+            if (sidx < K && (sidx % dilation) == 0) {
+                const int o = sidx / dilation;
+                out0[(size_t)i * kout + o] = (h == 0) ? L.i0 : L.i1;
+                out1[(size_t)i * kout + o] = i;
+            }
+        }
+    }
+}
+
+size_t knn_fast_smem(int C) {
+    return ((size_t)C * XLD + 2 * FKC * XLD + TQ * DLD + TQ + TK) * sizeof(float);
+}
+
 }  // namespace
 
 extern "C" size_t ge_knn_graph_workspace_bytes(int B, int C, int N, int M) {
-    (void)C;
-    if (B <= 0 || N <= 0 || M <= 0) return 0;
-    return (size_t)2 * B * ((size_t)N + M) * sizeof(float);
+    if (B <= 0 || C <= 0 || N <= 0 || M <= 0) return 0;
+    // normalised copies of x and y + their squared norms
+    return ((size_t)B * C * ((size_t)N + M) + (size_t)B * ((size_t)N + M)) * sizeof(float);
 }
 
 extern "C" int ge_knn_graph(const float* x, const float* y, const float* relative_pos, long long* edge_index,
@@ -227,20 +377,34 @@ extern "C" int ge_knn_graph(const float* x, const float* y, const float* relativ
     GE_REQUIRE(y != nullptr || N == M, GE_ERR_SHAPE, "ge_knn_graph: self-graph needs M == N");
     GE_REQUIRE(workspace_bytes >= ge_knn_graph_workspace_bytes(B, C, N, M), GE_ERR_ARG, "ge_knn_graph: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    float* xden = static_cast<float*>(workspace);
-    float* xsq = xden + (size_t)B * N;
-    float* yden = xsq + (size_t)B * N;
-    float* ysq = yden + (size_t)B * M;
-    knn_norm_kernel<<<dim3(ge::cdiv(N, 128), B), 128, 0, st>>>(x, xden, xsq, C, N);
+    float* xn = static_cast<float*>(workspace);
+    float* yn = xn + (size_t)B * C * N;
+    float* xsq = yn + (size_t)B * C * M;
+    float* ysq = xsq + (size_t)B * N;
+    knn_norm_kernel<<<dim3(ge::cdiv(N, 128), B), 128, 0, st>>>(x, xn, xsq, C, N);
     GE_CHECK_LAUNCH("ge_knn_graph(norm x)");
     if (y != nullptr) {
-        knn_norm_kernel<<<dim3(ge::cdiv(M, 128), B), 128, 0, st>>>(y, yden, ysq, C, M);
+        knn_norm_kernel<<<dim3(ge::cdiv(M, 128), B), 128, 0, st>>>(y, yn, ysq, C, M);
         GE_CHECK_LAUNCH("ge_knn_graph(norm y)");
     } else {
-        yden = xden; ysq = xsq; y = x;
+        yn = xn; ysq = xsq;
     }
-    knn_graph_kernel<<<dim3(ge::cdiv(N, TQ), B), KNN_THREADS, 0, st>>>(x, y, xden, xsq, yden, ysq, relative_pos,
-                                                                       edge_index, B, C, N, M, K, dilation);
+    const size_t smem = knn_fast_smem(C);
+    const bool fast = (N % 4 == 0) && (M % 4 == 0) && (C % FKC == 0) && smem <= 110 * 1024 &&
+                      (reinterpret_cast<uintptr_t>(xn) % 16 == 0);
+    if (fast) {
+        static size_t cached = 0;
+        if (smem > cached) {
+            GE_CUDA(cudaFuncSetAttribute(knn_graph_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                    "ge_knn_graph(attr)");
+            cached = smem;
+        }
+        knn_graph_fast_kernel<<<dim3(ge::cdiv(N, TQ), B), KNN_THREADS, smem, st>>>(xn, yn, xsq, ysq, relative_pos,
+                                                                                   edge_index, B, C, N, M, K, dilation);
+    } else {
+        knn_graph_kernel<<<dim3(ge::cdiv(N, TQ), B), KNN_THREADS, 0, st>>>(xn, yn, xsq, ysq, relative_pos,
+                                                                           edge_index, B, C, N, M, K, dilation);
+    }
     GE_CHECK_LAUNCH("ge_knn_graph");
     return GE_OK;
 }

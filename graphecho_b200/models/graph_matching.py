@@ -20,6 +20,14 @@ from .transformer import MultiHeadAttention
 INF = 100000000
 
 
+class _null_ctx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
 class BCEFocalLoss(nn.Module):
     """Focal BCE on probabilities (graph_matching.py:23-45)."""
 
@@ -74,6 +82,8 @@ class GModule(nn.Module):
         self.with_score_weight = False
         # 'sklearn' = the reference's CPU SpectralClustering round trip; 'device' = on-GPU bipartition
         self.cluster_backend = "sklearn"
+        self.async_seed_update = True
+        self._seed_stream = None
 
         self.graph_generator = PrototypeComputation(num_classes)
         self.head_in_cfg = "LN"
@@ -122,6 +132,7 @@ class GModule(nn.Module):
     def _train_fp32(self, features, targets, score_maps):
         features_s, features_t = features
         losses = {}
+        self._sync_seed_stream()
         nodes_1, labels_1, weights_1 = self.graph_generator(
             self.compute_locations(features_s), features_s, self.find_bbox(targets))
         nodes_2, labels_2, weights_2 = self.graph_generator(
@@ -192,6 +203,9 @@ class GModule(nn.Module):
                 continue
             SL.append(torch.full((len(S[-1]),), float(c), device=dev))
             TL.append(torch.full((len(T[-1]),), float(c), device=dev))
+        # class-major layout of the regrouped nodes, known on the host: update_seed needs no further sync
+        kept = [int(c) for c in present if s_cnt[int(c)] > 0 or t_cnt[int(c)] > 0]
+        self._class_layout = [(c, len(s_), len(t_)) for c, s_, t_ in zip(kept, S, T)]
         return (torch.cat(S), torch.cat(T)), (torch.cat(SL), torch.cat(TL)), (torch.cat(SW), torch.cat(TW))
 
     def _forward_preprocessing_source(self, sr_nodes, sr_nodes_label):
@@ -267,15 +281,44 @@ class GModule(nn.Module):
     @torch.no_grad()
     def update_seed(self, sr_nodes, sr_labels, tg_nodes=None, tg_labels=None):
         """graph_matching.py:532-567: per class, mean of the (spectrally filtered) nodes blended into
-        the seed bank with cosine-similarity momentum."""
-        self._update_bank(sr_nodes, sr_labels, self.sr_seed)
-        if tg_nodes is not None:
-            self._update_bank(tg_nodes, tg_labels, self.tg_seed)
+        the seed bank with cosine-similarity momentum.  The banks are only read by the NEXT step's
+        hallucination, so on CUDA the update runs on a side stream, overlapped with the rest of the step
+        (`_sync_seed_stream` joins it before the banks are read again)."""
+        side = None
+        if sr_nodes.is_cuda and self.cluster_backend == "device" and self.async_seed_update:
+            if self._seed_stream is None:
+                self._seed_stream = torch.cuda.Stream(device=sr_nodes.device)
+            side = self._seed_stream
+            side.wait_stream(torch.cuda.current_stream())
+            for t in (sr_nodes, sr_labels, tg_nodes, tg_labels):
+                if t is not None:
+                    t.record_stream(side)
+        layout = getattr(self, "_class_layout", None)
+        if layout is not None and (sum(l[1] for l in layout) != sr_nodes.size(0) or
+                                   (tg_nodes is not None and sum(l[2] for l in layout) != tg_nodes.size(0))):
+            layout = None
+        with torch.cuda.stream(side) if side is not None else _null_ctx():
+            self._update_bank(sr_nodes, sr_labels, self.sr_seed, None if layout is None else [(c, a) for c, a, _ in layout])
+            if tg_nodes is not None:
+                self._update_bank(tg_nodes, tg_labels, self.tg_seed,
+                                  None if layout is None else [(c, b) for c, _, b in layout])
+        self._class_layout = None
 
-    def _update_bank(self, nodes, labels, bank, k=20):
+    def _sync_seed_stream(self):
+        if self._seed_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._seed_stream)
+
+    def _update_bank(self, nodes, labels, bank, layout=None, k=20):
         nodes = nodes.detach()
-        for cls in labels.unique().long().tolist():
-            bs = nodes[labels == cls]
+        if layout is None:
+            layout = [(cls, None) for cls in labels.unique().long().tolist()]
+        off = 0
+        for cls, count in layout:
+            if count is None:
+                bs = nodes[labels == cls]
+            else:
+                bs = nodes[off:off + count]       # regrouped class-major: a contiguous slice, no sync
+                off += count
             if len(bs) > k and self.with_cluster_update:
                 keep = self._bipartition(torch.cat([bank[cls][None, :], bs]))
                 bs = bs[keep]

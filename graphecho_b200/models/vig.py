@@ -245,11 +245,12 @@ class Grapher(nn.Module):
 
     def forward(self, x):
         shortcut = x
-        x = self.fc1(x)
+        x = GF.bn_act(self.fc1[0](x), self.fc1[1], relu=False)
         _, _, H, W = x.shape
         x = self.graph_conv(x, self._get_relative_pos(self.relative_pos, H, W))
-        x = self.fc2(x)
-        return self.drop_path(x) + shortcut
+        if isinstance(self.drop_path, nn.Identity):
+            return GF.bn_act(self.fc2[0](x), self.fc2[1], residual=shortcut, relu=False)   # BN + residual in one pass
+        return self.drop_path(GF.bn_act(self.fc2[0](x), self.fc2[1], relu=False)) + shortcut
 
 
 def act_layer(act, inplace=False, neg_slope=0.2, n_prelu=1):

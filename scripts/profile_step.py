@@ -19,7 +19,12 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(2): step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+rows = [e for e in prof.key_averages() if e.self_device_time_total > 0]
+rows.sort(key=lambda e: -e.self_device_time_total)
+tot = sum(e.self_device_time_total for e in rows)
+print("total self device ms per step", tot / 2e3)
+for e in rows[:45]:
+    print(f"{e.self_device_time_total/2e3:8.3f} ms {100*e.self_device_time_total/tot:5.1f}% {e.count//2:5d}  {e.key[:110]}")
 import time
 t0 = time.perf_counter()
 for _ in range(5): step()
