@@ -126,6 +126,19 @@ def init_distributed(device_index: int | None = None):
     return rank, local, world
 
 
+class _JointDiscriminator(nn.Module):
+    """Discriminator fed the whole [source | target] feature map of a level (no slice + cat)."""
+
+    def __init__(self, dis: Discriminator):
+        super().__init__()
+        self.dis = dis
+        self.n_source = None          # frames of the source stream at the front of the batch (default: half)
+
+    def forward(self, feature_all):
+        ns = feature_all.shape[0] // 2 if self.n_source is None else self.n_source
+        return self.dis.forward_joint(feature_all, ns)
+
+
 class UDAEngine:
     def __init__(self, cfg: EngineConfig, device: torch.device, world_size: int = 1):
         self.cfg, self.device, self.world = cfg, device, world_size
@@ -140,10 +153,11 @@ class UDAEngine:
             gm = GModule(in_channels=256, num_classes=nc, device=device).to(device)
             gm.cluster_backend = cfg.cluster_backend
             self.aux["Graph"] = gm
+            self._gmodule = gm
         if cfg.discriminator and cfg.graph_matching:
             for lvl in ("p2", "p3", "p4", "p5"):
-                self.aux[f"Dis_{lvl.upper()}"] = Discriminator(grad_reverse_lambda=0.02).to(device).to(
-                    memory_format=torch.channels_last)
+                self.aux[f"Dis_{lvl.upper()}"] = _JointDiscriminator(
+                    Discriminator(grad_reverse_lambda=0.02).to(device).to(memory_format=torch.channels_last))
         if cfg.vig_grapher:
             self.aux["Grapher"] = Grapher(256, 9, 1, "mr", "gelu", "batch", True, False, 0.0, 1,
                                           (cfg.hw // 4) ** 2, 0.0, False).to(device)
@@ -187,7 +201,7 @@ class UDAEngine:
             for i, lvl in enumerate(("P2", "P3", "P4", "P5")):
                 f = feats[i]
                 calls.append(self.aux[f"Dis_{lvl}"])
-                samples.append(((torch.zeros_like(f[:ns]).requires_grad_(), torch.zeros_like(f[ns:]).requires_grad_()),))
+                samples.append((torch.zeros_like(f).requires_grad_(),))
                 names.append(f"Dis_{lvl}")
         del feats
         from . import _cabi
@@ -216,6 +230,11 @@ class UDAEngine:
         cfg = self.cfg
         ns = frames_src.shape[0]
         losses = {}
+        for m in self.aux.values():
+            if isinstance(m, _JointDiscriminator):
+                if self.graphed and m.n_source not in (None, ns):
+                    raise RuntimeError("the source/target split changed after CUDA-graph capture")
+                m.n_source = ns
         if cfg.cuda_graphs and not self.graphed:
             self.capture_graphs(frames_src.shape[0] + frames_tgt.shape[0])
         with self._autocast():
@@ -227,14 +246,14 @@ class UDAEngine:
         if cfg.vig_grapher:
             with self._autocast():
                 feats = [self.aux["Grapher"](feats[0])] + list(feats[1:])
-        fs, ft = [f[:ns] for f in feats], [f[ns:] for f in feats]
         score_maps = torch.where(torch.sigmoid(pred_t) > 0.5, 1, 0)                # train_cardiac_uda.py:235
-        (fs, ft), nodes, mid = self.aux["Graph"](None, (fs, ft), targets=masks_src, score_maps=score_maps)
+        # source frames first, target frames after: the joint entry points avoid slicing the pyramid
+        _, nodes, mid = self._gmodule.forward_joint(feats, ns, masks_src, score_maps)
         losses.update(mid)
         if cfg.discriminator:
             with self._autocast():
                 for i, lvl in enumerate(("p2", "p3", "p4", "p5")):
-                    losses[f"loss_adv_{lvl}"] = 0.1 * self.aux[f"Dis_{lvl.upper()}"]((fs[i], ft[i]))
+                    losses[f"loss_adv_{lvl}"] = 0.1 * self.aux[f"Dis_{lvl.upper()}"](feats[i])
         if cfg.temporal_graph and clips_shape is not None and nodes[0].numel() > 0 and nodes[0].dim() == 2:
             b, t = clips_shape                                                      # train_cardiac_uda.py:300-304
             graph_features = [f.reshape(b, t, *f.shape[1:]) for f in feats]

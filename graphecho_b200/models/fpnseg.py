@@ -235,6 +235,15 @@ class Discriminator(nn.Module):
             x = GF.gn_relu(conv(x), gn.weight, gn.bias, gn.num_groups, gn.eps)
         return self.cls_logits(x).float()
 
+    def forward_joint(self, feature_all, n_source):
+        """forward((feature_all[:n_source], feature_all[n_source:])) without slicing / re-concatenating the
+        feature map (the source frames come first): only the small logit map is split."""
+        _need_cuda(feature_all)
+        x = self._tower(self.grad_reverse(feature_all))
+        xs, xt = x[:n_source], x[n_source:]
+        return self.loss_fn(xs, torch.full_like(xs, self.source_label)) + \
+            self.loss_fn(xt, torch.full_like(xt, self.target_label))
+
     def forward(self, feature, domain="source"):
         fs, ft = feature
         _need_cuda(fs)

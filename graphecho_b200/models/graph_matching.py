@@ -28,6 +28,14 @@ class _null_ctx:
         return False
 
 
+def _nonzero_known(mask, count):
+    """Indices of the True entries of a 1-D mask whose count is already known on the host: no
+    device->host sync (torch.nonzero has to read the count back)."""
+    if hasattr(torch, "nonzero_static"):
+        return torch.nonzero_static(mask, size=int(count)).squeeze(1)
+    return torch.nonzero(mask).squeeze(1)
+
+
 class BCEFocalLoss(nn.Module):
     """Focal BCE on probabilities (graph_matching.py:23-45)."""
 
@@ -127,16 +135,28 @@ class GModule(nn.Module):
 
     def _forward_train(self, images, features, targets=None, score_maps=None):
         with torch.autocast("cuda", enabled=False):
-            return self._train_fp32(features, targets, score_maps)
+            features_s, features_t = features
+            return self._train_fp32(features, (features_s, 0), (features_t, 0), targets, score_maps)
 
-    def _train_fp32(self, features, targets, score_maps):
-        features_s, features_t = features
+    def forward_joint(self, features_all, n_source, targets, score_maps):
+        """Same as forward(images, (features_all[:n_source], features_all[n_source:]), targets, score_maps)
+        for features that hold the source frames first and the target frames after them, WITHOUT slicing
+        the feature maps: nodes are gathered from the full tensors with a batch offset, so autograd never
+        materialises zero-padded slice gradients of the pyramid."""
+        with torch.autocast("cuda", enabled=False):
+            return self._train_fp32(None, (features_all, 0), (features_all, int(n_source)), targets, score_maps)
+
+    def _train_fp32(self, features, src, tgt, targets, score_maps):
         losses = {}
         self._sync_seed_stream()
-        nodes_1, labels_1, weights_1 = self.graph_generator(
-            self.compute_locations(features_s), features_s, self.find_bbox(targets))
-        nodes_2, labels_2, weights_2 = self.graph_generator(
-            self.compute_locations(features_t), features_t, self.find_bbox(score_maps))
+        (feat_s, off_s), (feat_t, off_t) = src, tgt
+        boxes_s, boxes_t = self.find_bbox(targets), self.find_bbox(score_maps)
+        gen = self.graph_generator
+        plan_s = gen.plan(self.compute_locations(feat_s), boxes_s)
+        plan_t = gen.plan(self.compute_locations(feat_t), boxes_t)
+        counts = torch.stack([plan_s[1], plan_t[1]]).tolist()                      # ONE host sync for both domains
+        nodes_1, labels_1, weights_1 = gen.gather(feat_s, plan_s[0], counts[0], off_s)
+        nodes_2, labels_2, weights_2 = gen.gather(feat_t, plan_t[0], counts[1], off_t)
         if nodes_1.size(0) < 6 or nodes_1.dim() == 1:                             # graph_matching.py:259-260
             return features, (nodes_1, nodes_2), losses
         nodes_1, nodes_2 = nodes_1.float(), nodes_2.float()
@@ -182,29 +202,34 @@ class GModule(nn.Module):
         hallucinated from the other domain's seed bank (graph_matching.py:381-483)."""
         (sn, tn), (sl, tl), (sw, tw) = nodes, labels, weights
         dev = sn.device
-        present = torch.cat([sl, tl]).unique().tolist()                            # one host sync
-        s_cnt = torch.bincount(sl.long(), minlength=self.num_classes).tolist()
-        t_cnt = torch.bincount(tl.long(), minlength=self.num_classes).tolist()
+        nbin = max(self.num_classes, 1)
+        cnt = torch.stack([torch.bincount(sl.long(), minlength=nbin)[:nbin],
+                           torch.bincount(tl.long(), minlength=nbin)[:nbin]]).tolist()          # one host sync
+        s_cnt, t_cnt = cnt
+        present = [c for c in range(nbin) if s_cnt[c] > 0 or t_cnt[c] > 0]
         S, T, SL, TL, SW, TW = [], [], [], [], [], []
         for c in present:
             ci = int(c)
             has_s, has_t = s_cnt[ci] > 0, t_cnt[ci] > 0
-            s_c, t_c = sn[sl == c], tn[tl == c]
+            si = _nonzero_known(sl == c, s_cnt[ci]) if has_s else None
+            ti = _nonzero_known(tl == c, t_cnt[ci]) if has_t else None
+            s_c = sn[si] if has_s else None
+            t_c = tn[ti] if has_t else None
             if has_s and has_t:
                 S.append(s_c); T.append(t_c)
-                SW.append(sw[sl == c]); TW.append(tw[tl == c])
+                SW.append(sw[si]); TW.append(tw[ti])
             elif has_t:
                 S.append(self._hallucinate(self.sr_seed[ci], t_c)); T.append(t_c)
-                SW.append(torch.ones(len(t_c), dtype=torch.long, device=dev)); TW.append(tw[tl == c])
+                SW.append(torch.ones(len(t_c), dtype=torch.long, device=dev)); TW.append(tw[ti])
             elif has_s:
                 S.append(s_c); T.append(self._hallucinate(self.tg_seed[ci], s_c))
-                SW.append(sw[sl == c]); TW.append(torch.ones(len(s_c), dtype=torch.long, device=dev))
+                SW.append(sw[si]); TW.append(torch.ones(len(s_c), dtype=torch.long, device=dev))
             else:
                 continue
             SL.append(torch.full((len(S[-1]),), float(c), device=dev))
             TL.append(torch.full((len(T[-1]),), float(c), device=dev))
         # class-major layout of the regrouped nodes, known on the host: update_seed needs no further sync
-        kept = [int(c) for c in present if s_cnt[int(c)] > 0 or t_cnt[int(c)] > 0]
+        kept = [int(c) for c in present]
         self._class_layout = [(c, len(s_), len(t_)) for c, s_, t_ in zip(kept, S, T)]
         return (torch.cat(S), torch.cat(T)), (torch.cat(SL), torch.cat(TL)), (torch.cat(SW), torch.cat(TW))
 
@@ -247,11 +272,16 @@ class GModule(nn.Module):
         same = labels_side1.long().unsqueeze(1) == labels_side2.long().unsqueeze(0)     # one_hot @ one_hot^T == 1
         if self.matching_cfg == "o2o":
             M = GF.sinkhorn_rpm_exp(M, 20, True)
-            idx = (M * same.float()).max(-1)[1]
+            samef = same.float()
+            idx = (M * samef).max(-1)[1]
             tp = M.gather(1, idx.unsqueeze(1))
-            fp = M[~same].view(-1, 1)
             tp_loss = self.matching_loss(tp, torch.ones_like(tp)) / len(tp)
-            fp_loss = self.matching_loss(fp, torch.zeros_like(fp)) / fp.sum().detach()
+            # false positives = every different-class entry (graph_matching.py:582-588), reduced through the
+            # mask instead of a boolean gather (no host sync): mean focal loss over them / their sum
+            diff = 1.0 - samef
+            a, g = self.matching_loss.alpha, self.matching_loss.gamma
+            fp_elem = -(1 - a) * M ** g * torch.log(1 - M)
+            fp_loss = (fp_elem * diff).sum() / diff.sum() / (M * diff).sum().detach()
             return tp_loss + fp_loss, M
         if self.matching_cfg == "m2m":
             return self.matching_loss(M.sigmoid(), same.float()).mean(), M
@@ -411,35 +441,47 @@ class PrototypeComputation(object):
         labels[amin == INF] = 0
         return labels
 
-    def __call__(self, locations, features, targets):
-        if not locations:
-            raise NotImplementedError("the score-map sampling branch (graph_matching.py:1016-1065) is unreachable "
-                                      "from the reference trainers and is not on the accelerated path")
+    def plan(self, locations, boxes):
+        """Device-side half of the sampler: per-level label maps + the [levels, 2] (positive, negative)
+        counts the host needs.  No synchronisation."""
+        labels = [l.reshape(-1) for l in self.prepare_targets(locations, boxes)]
+        counts = torch.stack([torch.stack([(l > 0).sum(), (l == 0).sum()]) for l in labels])
+        return labels, counts
+
+    def gather(self, features, labels, counts, batch_offset=0):
+        """Host-driven half (graph_matching.py:978-1013) given the counts: strided positive picks,
+        floor(linspace) negative picks, row gathers from the NHWC feature maps.  `features` may hold more
+        images than were labelled; `batch_offset` is the index of the first labelled image."""
         C = features[0].size(1)
-        labels = self.prepare_targets(locations, targets)
         pos_pts, pos_lab, neg_pts = [], [], []
-        # one host sync for all per-level counts
-        counts = torch.stack([torch.stack([(l > 0).sum(), (l == 0).sum()]) for l in labels]).tolist()
         for l, lab in enumerate(labels):
-            lab = lab.reshape(-1)
-            flat = features[l].permute(0, 2, 3, 1).reshape(-1, C)
+            f = features[l]
+            flat = f.permute(0, 2, 3, 1).reshape(-1, C)
+            shift = batch_offset * f.size(2) * f.size(3)
             n_pos_all, n_neg_all = counts[l]
-            pos_idx = torch.nonzero(lab > 0).squeeze(1)
+            pos_idx = _nonzero_known(lab > 0, n_pos_all)
             step = n_pos_all // self.num_nodes_per_class
             if step > 1:
                 pos_idx = pos_idx[::step]
-            pos_pts.append(flat[pos_idx])
+            pos_pts.append(flat[pos_idx + shift])
             pos_lab.append(lab[pos_idx])
             num_pos = pos_idx.numel()
             if self.sample_bg_nodes:
-                neg_idx = torch.nonzero(lab == 0).squeeze(1)
+                neg_idx = _nonzero_known(lab == 0, n_neg_all)
                 if n_pos_all <= n_neg_all:
                     pick = np.floor(np.linspace(0, n_neg_all - 2, num_pos // self.bg_ratio)).astype(np.int64)
                     neg_idx = neg_idx[torch.as_tensor(pick, device=neg_idx.device)]
-                neg_pts.append(flat[neg_idx])
+                neg_pts.append(flat[neg_idx + shift])
         pos_pts, pos_lab = torch.cat(pos_pts, dim=0), torch.cat(pos_lab, dim=0)
         if self.sample_bg_nodes:
             neg_pts = torch.cat(neg_pts, dim=0)
             pos_pts = torch.cat([neg_pts, pos_pts], dim=0)
             pos_lab = torch.cat([pos_lab.new_zeros(neg_pts.size(0)), pos_lab])
         return pos_pts, pos_lab, torch.ones_like(pos_lab).long()
+
+    def __call__(self, locations, features, targets):
+        if not locations:
+            raise NotImplementedError("the score-map sampling branch (graph_matching.py:1016-1065) is unreachable "
+                                      "from the reference trainers and is not on the accelerated path")
+        labels, counts = self.plan(locations, targets)
+        return self.gather(features, labels, counts.tolist(), 0)

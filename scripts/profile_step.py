@@ -19,12 +19,17 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(2): step()
     torch.cuda.synchronize()
-rows = [e for e in prof.key_averages() if e.self_device_time_total > 0]
-rows.sort(key=lambda e: -e.self_device_time_total)
-tot = sum(e.self_device_time_total for e in rows)
-print("total self device ms per step", tot / 2e3)
-for e in rows[:45]:
-    print(f"{e.self_device_time_total/2e3:8.3f} ms {100*e.self_device_time_total/tot:5.1f}% {e.count//2:5d}  {e.key[:110]}")
+from torch.autograd import DeviceType
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0])
+for evt in prof.events():
+    if evt.device_type == DeviceType.CUDA:
+        agg[evt.name][0] += 1
+        agg[evt.name][1] += evt.device_time_total if hasattr(evt, "device_time_total") else evt.cuda_time_total
+tot = sum(v[1] for v in agg.values())
+print("GPU kernel ms per step", tot / 2e3, "kernels per step", sum(v[0] for v in agg.values()) // 2)
+for name, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+    print(f"{v[1]/2e3:8.3f} ms {100*v[1]/tot:5.1f}% {v[0]//2:5d}  {name[:120]}")
 import time
 t0 = time.perf_counter()
 for _ in range(5): step()

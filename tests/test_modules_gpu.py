@@ -187,6 +187,37 @@ def test_gmodule_train_step(dev, golden, backend):
     assert torch.equal(gm.find_bbox(masks)[1].cpu(), s["boxes"])
 
 
+def test_joint_entry_points_equal_the_sliced_api(dev):
+    """GModule.forward_joint / Discriminator.forward_joint (no slicing of the pyramid) give the same
+    losses and gradients as the reference-shaped API on (features[:ns], features[ns:])."""
+    B, hw, nc = 2, 256, 3
+    feats = [torch.cat([a, b]).to(dev).contiguous(memory_format=torch.channels_last)
+             for a, b in zip(synth.pyramid(B, hw, seed=21), synth.pyramid(B, hw, seed=22))]
+    masks, score = synth.disc_masks(B, nc, hw).to(dev), synth.disc_masks(B, nc, hw, shift=6).to(dev)
+    res = []
+    for joint in (False, True):
+        gm = no_dropout(fill_module(quiet(graph_matching.GModule, 256, nc, dev))).to(dev).train()
+        gm.cluster_backend, gm.async_seed_update = "device", False
+        dis = fill_module(fpnseg.Discriminator(grad_reverse_lambda=0.02), prefix="dis.").to(dev)
+        f = [t.clone().requires_grad_() for t in feats]
+        if joint:
+            _, nodes, losses = gm.forward_joint(f, B, masks, score)
+            adv = dis.forward_joint(f[2], B)
+        else:
+            _, nodes, losses = gm(None, ([t[:B] for t in f], [t[B:] for t in f]), targets=masks, score_maps=score)
+            adv = dis((f[2][:B], f[2][B:]))
+        (sum(losses.values()) + adv).backward()
+        res.append((losses, adv, [t.grad for t in f], nodes))
+    (l0, a0, g0, n0), (l1, a1, g1, n1) = res
+    assert set(l0) == set(l1)
+    for k in l0:
+        close(l1[k], l0[k], rtol=1e-5, atol=1e-7)
+    close(a1, a0, rtol=1e-5, atol=1e-7)
+    close(n1[0], n0[0], rtol=1e-5, atol=1e-6)
+    for x, y in zip(g1, g0):
+        close(x, y, rtol=1e-4, atol=1e-8)
+
+
 def test_gmodule_no_nodes_early_return(dev):
     """num_classes=1: every location is background -> no nodes -> empty loss dict (Appendix A-1)."""
     gm = quiet(graph_matching.GModule, 256, 1, dev).to(dev).train()
