@@ -49,6 +49,7 @@ class EngineConfig:
     weight_decay: float = 1e-4
     cluster_backend: str = "device"     # GModule.update_seed bipartition: 'device' | 'sklearn'
     cuda_graphs: bool = False           # capture the static segments (FPN, Grapher, discriminators) as CUDA graphs
+    overlap_streams: bool = True        # GModule on a side stream, overlapped with the discriminators
     seed: int = 0
 
 
@@ -126,6 +127,14 @@ def init_distributed(device_index: int | None = None):
     return rank, local, world
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
 class _JointDiscriminator(nn.Module):
     """Discriminator fed the whole [source | target] feature map of a level (no slice + cat)."""
 
@@ -171,6 +180,7 @@ class UDAEngine:
             m.train()
         self.grads = FlatGradSync(modules)
         self.graphed = False
+        self._side_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
         self.graph_launches = 0      # graphecho_b200 kernels replayed per step inside the CUDA graphs
         self.opt = {"Net": torch.optim.Adam(self.network.parameters(), lr=cfg.lr_net, betas=(0.9, 0.999),
                                             weight_decay=cfg.weight_decay, fused=device.type == "cuda")}
@@ -247,13 +257,25 @@ class UDAEngine:
             with self._autocast():
                 feats = [self.aux["Grapher"](feats[0])] + list(feats[1:])
         score_maps = torch.where(torch.sigmoid(pred_t) > 0.5, 1, 0)                # train_cardiac_uda.py:235
-        # source frames first, target frames after: the joint entry points avoid slicing the pyramid
-        _, nodes, mid = self._gmodule.forward_joint(feats, ns, masks_src, score_maps)
-        losses.update(mid)
+        # The graph-matching module is host-driven (two count read-backs, hundreds of tiny launches) while
+        # the discriminators are four long GPU-bound graph replays with no dependency on it: run GModule on
+        # a side stream so its host synchronisations wait only for its own small kernels and its launch
+        # latency hides under the discriminator towers.  Autograd replays each backward on its forward
+        # stream, so the same overlap happens in the backward pass.
+        main = torch.cuda.current_stream()
+        side = self._side_stream if cfg.overlap_streams else None
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side) if side is not None else _NullCtx():
+            # source frames first, target frames after: the joint entry points avoid slicing the pyramid
+            _, nodes, mid = self._gmodule.forward_joint(feats, ns, masks_src, score_maps)
         if cfg.discriminator:
             with self._autocast():
                 for i, lvl in enumerate(("p2", "p3", "p4", "p5")):
                     losses[f"loss_adv_{lvl}"] = 0.1 * self.aux[f"Dis_{lvl.upper()}"](feats[i])
+        if side is not None:
+            main.wait_stream(side)
+        losses.update(mid)
         if cfg.temporal_graph and clips_shape is not None and nodes[0].numel() > 0 and nodes[0].dim() == 2:
             b, t = clips_shape                                                      # train_cardiac_uda.py:300-304
             graph_features = [f.reshape(b, t, *f.shape[1:]) for f in feats]
