@@ -109,35 +109,49 @@ bn_finalize_stats_kernel(const float* __restrict__ part, int nparts, const float
 
 // ---- stage 3 (forward): out = act( x*sc + sh (+ residual) ) --------------------------------------
 // MODE 0: training (sc/sh from save_mean/save_rstd); MODE 1: inference (from running stats, `rstd` = var)
+// A thread owns one channel octet of PIX consecutive pixels: the per-channel constants are loaded once
+// and PIX independent 128-bit loads are in flight before the first use.
+constexpr int PIX = 4;
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 bn_apply_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ mean,
                     const float* __restrict__ rstd_or_var, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, T* __restrict__ out, int C, float eps, int relu, long long total8) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total8) return;
+                    const float* __restrict__ beta, T* __restrict__ out, long long P, int C, float eps, int relu) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c8 = C >> 3;
-    const int cc = (int)(e % c8) * 8;
-    float m[8], r[8], g[8], b[8], v[8], o[8];
+    const int cc = (int)(t % c8) * 8;
+    const long long p0 = (t / c8) * PIX;
+    if (p0 >= P) return;
+    float m[8], r[8], g[8], b[8], sc[8], sh[8];
     load8f(mean + cc, m); load8f(rstd_or_var + cc, r); load8f(gamma + cc, g); load8f(beta + cc, b);
-    load8<T>(x + e * 8, v);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const float rs = (MODE == 0) ? r[u] : 1.f / sqrtf(r[u] + eps);
-        const float sc = rs * g[u];
-        o[u] = fmaf(v[u], sc, b[u] - m[u] * sc);
+        sc[u] = rs * g[u];
+        sh[u] = b[u] - m[u] * sc[u];
     }
+    float v[PIX][8], rv[PIX][8];
+#pragma unroll
+    for (int q = 0; q < PIX; ++q)
+        if (p0 + q < P) load8<T>(x + (p0 + q) * C + cc, v[q]);
     if (res != nullptr) {
-        float rv[8];
-        load8<T>(res + e * 8, rv);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) o[u] += rv[u];
+        for (int q = 0; q < PIX; ++q)
+            if (p0 + q < P) load8<T>(res + (p0 + q) * C + cc, rv[q]);
     }
-    if (relu) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) o[u] = fmaxf(o[u], 0.f);
+    for (int q = 0; q < PIX; ++q) {
+        if (p0 + q >= P) break;
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            o[u] = fmaf(v[q][u], sc[u], sh[u]);
+            if (res != nullptr) o[u] += rv[q][u];
+            if (relu) o[u] = fmaxf(o[u], 0.f);
+        }
+        store8<T>(out + (p0 + q) * C + cc, o);
     }
-    store8<T>(out + e * 8, o);
 }
 
 // ---- backward stage 1: partial sums of dyr = dy * relu'(out) and dyr * xhat ----------------------
@@ -201,43 +215,53 @@ bn_finalize_bwd_kernel(const float* __restrict__ part, int nparts, float* __rest
     dgamma[c] = sb;
 }
 
-// ---- backward stage 3: dx = rstd*gamma*(dyr - S1/P - xhat*S2/P)   [training]
-//                        dx = dyr * gamma / sqrt(var+eps)            [inference];  dres = dyr ----------
-template <typename T, int MODE>
+// ---- backward stage 3: dx = rstd*gamma*(dyr - S1/P - xhat*S2/P);  dres = dyr ------------------------
+constexpr int BPIX = 2;   // three input streams per pixel: keep the register footprint under 128
+
+template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ out, const T* __restrict__ x,
-                    const float* __restrict__ mean, const float* __restrict__ rstd_or_var,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ dgamma,
                     const float* __restrict__ dbeta, T* __restrict__ dx, T* __restrict__ dres,
-                    int C, float eps, float invP, int relu, long long total8) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total8) return;
+                    long long P, int C, float invP, int relu) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c8 = C >> 3;
-    const int cc = (int)(e % c8) * 8;
-    float m[8], r[8], g[8], gv[8], o[8];
-    load8f(mean + cc, m); load8f(rstd_or_var + cc, r); load8f(gamma + cc, g);
-    load8<T>(dy + e * 8, gv);
-    if (relu) {
-        float ov[8];
-        load8<T>(out + e * 8, ov);
+    const int cc = (int)(t % c8) * 8;
+    const long long p0 = (t / c8) * BPIX;
+    if (p0 >= P) return;
+    float m[8], r[8], g[8], s1[8], s2[8], k0[8], k1[8], k2[8];
+    load8f(mean + cc, m); load8f(rstd + cc, r); load8f(gamma + cc, g);
+    load8f(dbeta + cc, s1); load8f(dgamma + cc, s2);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) gv[u] = (ov[u] > 0.f) ? gv[u] : 0.f;
+    for (int u = 0; u < 8; ++u) {       // dx = k0*dyr - k1 - xhat*k2
+        k0[u] = r[u] * g[u];
+        k1[u] = k0[u] * s1[u] * invP;
+        k2[u] = k0[u] * s2[u] * invP;
     }
-    if (dres != nullptr) store8<T>(dres + e * 8, gv);
-    if (MODE == 0) {
-        float s1[8], s2[8], xv[8];
-        load8f(dbeta + cc, s1); load8f(dgamma + cc, s2);
-        load8<T>(x + e * 8, xv);
+    float gv[BPIX][8], xv[BPIX][8], ov[BPIX][8];
+#pragma unroll
+    for (int q = 0; q < BPIX; ++q)
+        if (p0 + q < P) { load8<T>(dy + (p0 + q) * C + cc, gv[q]); load8<T>(x + (p0 + q) * C + cc, xv[q]); }
+    if (relu) {
+#pragma unroll
+        for (int q = 0; q < BPIX; ++q)
+            if (p0 + q < P) load8<T>(out + (p0 + q) * C + cc, ov[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < BPIX; ++q) {
+        if (p0 + q >= P) break;
+        float o[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const float xh = (xv[u] - m[u]) * r[u];
-            o[u] = r[u] * g[u] * (gv[u] - s1[u] * invP - xh * s2[u] * invP);
+            const float gq = (relu && !(ov[q][u] > 0.f)) ? 0.f : gv[q][u];
+            gv[q][u] = gq;
+            const float xh = (xv[q][u] - m[u]) * r[u];
+            o[u] = k0[u] * gq - k1[u] - xh * k2[u];
         }
-    } else {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) o[u] = gv[u] * g[u] / sqrtf(r[u] + eps);
+        if (dres != nullptr) store8<T>(dres + (p0 + q) * C + cc, gv[q]);
+        store8<T>(dx + (p0 + q) * C + cc, o);
     }
-    store8<T>(dx + e * 8, o);
 }
 
 int bn_chunks(long long P, int C) {
@@ -278,7 +302,7 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
     // shift = running mean when tracked (close to the batch mean), else beta-free zero shift via gamma-less trick
     const float* shift = running_mean != nullptr ? running_mean : save_mean;
     if (running_mean == nullptr) GE_CUDA(cudaMemsetAsync(save_mean, 0, (size_t)C * sizeof(float), st), "ge_bn_fwd_train(memset)");
-    const long long total8 = P * (C / 8);
+    const long long total8 = ge::cdivll(P, PIX) * (C / 8);
     const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
     static size_t c0 = 0, c1 = 0;
     if (dtype == GE_DTYPE_F32) {
@@ -294,10 +318,10 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
     GE_CHECK_LAUNCH("ge_bn_fwd_train(finalize)");
     if (dtype == GE_DTYPE_F32)
         bn_apply_fwd_kernel<float, 0><<<blocks, 256, 0, st>>>((const float*)x, (const float*)residual, save_mean, save_rstd,
-                                                               gamma, beta, (float*)out, C, eps, relu, total8);
+                                                               gamma, beta, (float*)out, P, C, eps, relu);
     else
         bn_apply_fwd_kernel<bf16, 0><<<blocks, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, save_mean, save_rstd,
-                                                              gamma, beta, (bf16*)out, C, eps, relu, total8);
+                                                              gamma, beta, (bf16*)out, P, C, eps, relu);
     GE_CHECK_LAUNCH("ge_bn_fwd_train(apply)");
     return GE_OK;
 }
@@ -309,14 +333,14 @@ extern "C" int ge_bn_fwd_eval(const void* x, const void* residual, const float* 
     GE_REQUIRE(P > 0 && C > 0, GE_ERR_ARG, "ge_bn_fwd_eval: bad dimension");
     GE_REQUIRE(C % 8 == 0, GE_ERR_SHAPE, "ge_bn_fwd_eval: C=%d must be a multiple of 8", C);
     cudaStream_t st = (cudaStream_t)stream;
-    const long long total8 = P * (C / 8);
+    const long long total8 = ge::cdivll(P, PIX) * (C / 8);
     const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
     if (dtype == GE_DTYPE_F32)
         bn_apply_fwd_kernel<float, 1><<<blocks, 256, 0, st>>>((const float*)x, (const float*)residual, running_mean, running_var,
-                                                               gamma, beta, (float*)out, C, eps, relu, total8);
+                                                               gamma, beta, (float*)out, P, C, eps, relu);
     else if (dtype == GE_DTYPE_BF16)
         bn_apply_fwd_kernel<bf16, 1><<<blocks, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, running_mean, running_var,
-                                                              gamma, beta, (bf16*)out, C, eps, relu, total8);
+                                                              gamma, beta, (bf16*)out, P, C, eps, relu);
     else { ge_set_error("ge_bn_fwd_eval: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_bn_fwd_eval");
     return GE_OK;
@@ -339,7 +363,7 @@ extern "C" int ge_bn_bwd(const void* dy, const void* out, const void* x, const f
     const long long ppc = ge::cdivll(P, chunks);
     const size_t smem = bn_smem(C);
     float* part = static_cast<float*>(workspace);
-    const long long total8 = P * (C / 8);
+    const long long total8 = ge::cdivll(P, BPIX) * (C / 8);
     const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
     static size_t c0 = 0, c1 = 0;
     const float* rstd = rstd_or_var;
@@ -359,11 +383,11 @@ extern "C" int ge_bn_bwd(const void* dy, const void* out, const void* x, const f
     GE_CHECK_LAUNCH("ge_bn_bwd(finalize)");
     const float invP = 1.f / (float)P;
     if (dtype == GE_DTYPE_F32)
-        bn_apply_bwd_kernel<float, 0><<<blocks, 256, 0, st>>>((const float*)dy, (const float*)out, (const float*)x, mean, rstd,
-            gamma, dgamma, dbeta, (float*)dx, (float*)dres, C, eps, invP, relu, total8);
+        bn_apply_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, (const float*)out, (const float*)x, mean, rstd,
+            gamma, dgamma, dbeta, (float*)dx, (float*)dres, P, C, invP, relu);
     else
-        bn_apply_bwd_kernel<bf16, 0><<<blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)out, (const bf16*)x, mean, rstd,
-            gamma, dgamma, dbeta, (bf16*)dx, (bf16*)dres, C, eps, invP, relu, total8);
+        bn_apply_bwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)out, (const bf16*)x, mean, rstd,
+            gamma, dgamma, dbeta, (bf16*)dx, (bf16*)dres, P, C, invP, relu);
     GE_CHECK_LAUNCH("ge_bn_bwd(apply)");
     return GE_OK;
 }

@@ -103,33 +103,53 @@ __device__ __forceinline__ void affine8(const float* mean, const float* rstd, co
 }
 
 // ---- forward: out = bilinear_up(relu(gn(x)))  (same size = identity) ----------------------------
+// A thread owns one channel octet of GPIX consecutive output pixels of one sample (per-(n,c) constants
+// loaded once, GPIX independent 128-bit loads in flight).
+constexpr int GPIX = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 gn_relu_up_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ out,
-                      int h, int w, int H, int W, int C, long long total8) {
+                      int h, int w, int H, int W, int C, long long total) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total8) return;
+    if (e >= total) return;
     const int c8 = C >> 3;
     const int cc = (int)(e % c8) * 8;
-    long long p = e / c8;
-    const int ox = (int)(p % W); p /= W;
-    const int oy = (int)(p % H);
-    const int n = (int)(p / H);
-    float sc[8], sh[8], res[8];
+    const int HW = H * W;
+    const int groups = (HW + GPIX - 1) / GPIX;
+    const long long pg = e / c8;
+    const int n = (int)(pg / groups);
+    const int q0 = (int)(pg - (long long)n * groups) * GPIX;
+    float sc[8], sh[8];
     affine8(mean + (size_t)n * C + cc, rstd + (size_t)n * C + cc, gamma + cc, beta + cc, sc, sh);
     const T* xb = x + (size_t)n * h * w * C + cc;
+    T* ob = out + (size_t)n * HW * C + cc;
     if (h == H && w == W) {
-        float v[8];
-        load8<T>(xb + ((size_t)oy * w + ox) * C, v);
+        float v[GPIX][8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) res[u] = fmaxf(fmaf(v[u], sc[u], sh[u]), 0.f);
-    } else {
+        for (int q = 0; q < GPIX; ++q)
+            if (q0 + q < HW) load8<T>(xb + (size_t)(q0 + q) * C, v[q]);
+#pragma unroll
+        for (int q = 0; q < GPIX; ++q) {
+            if (q0 + q >= HW) break;
+            float res[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) res[u] = fmaxf(fmaf(v[q][u], sc[u], sh[u]), 0.f);
+            store8<T>(ob + (size_t)(q0 + q) * C, res);
+        }
+        return;
+    }
+    const float scy = ac_scale(h, H), scx = ac_scale(w, W);
+    for (int q = 0; q < GPIX; ++q) {
+        const int pix = q0 + q;
+        if (pix >= HW) break;
+        const int oy = pix / W, ox = pix - oy * W;
         int y0, y1, x0, x1; float ly, lx;
-        src_coord(oy, ac_scale(h, H), h, y0, y1, ly);
-        src_coord(ox, ac_scale(w, W), w, x0, x1, lx);
+        src_coord(oy, scy, h, y0, y1, ly);
+        src_coord(ox, scx, w, x0, x1, lx);
         const float hy = 1.f - ly, hx = 1.f - lx;
-        float a[8], b[8], c[8], d[8];
+        float a[8], b[8], c[8], d[8], res[8];
         load8<T>(xb + ((size_t)y0 * w + x0) * C, a);
         load8<T>(xb + ((size_t)y0 * w + x1) * C, b);
         load8<T>(xb + ((size_t)y1 * w + x0) * C, c);
@@ -140,8 +160,8 @@ gn_relu_up_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, c
             const float nc = fmaxf(fmaf(c[u], sc[u], sh[u]), 0.f), nd = fmaxf(fmaf(d[u], sc[u], sh[u]), 0.f);
             res[u] = hy * (hx * na + lx * nb) + ly * (hx * nc + lx * nd);
         }
+        store8<T>(ob + (size_t)pix * C, res);
     }
-    store8<T>(out + (((size_t)n * H + oy) * W + ox) * C + cc, res);
 }
 
 // gradient arriving at source pixel (sy,sx): identity or the adjoint of the bilinear gather
@@ -240,35 +260,44 @@ gn_relu_up_bwd_apply_kernel(const T* __restrict__ dout, const float* __restrict_
                             const float* __restrict__ mean, const float* __restrict__ rstd,
                             const float* __restrict__ gamma, const float* __restrict__ beta,
                             const float* __restrict__ A1, const float* __restrict__ A2, T* __restrict__ dx,
-                            int hw, int C, int ident, long long total8) {
+                            int hw, int C, int ident, long long total) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total8) return;
+    if (e >= total) return;
     const int c8 = C >> 3;
     const int cc = (int)(e % c8) * 8;
-    const long long p = e / c8;              // n*hw + pixel
-    const int n = (int)(p / hw);
-    float sc[8], sh[8], m[8], r[8], g[8], a1[8], a2[8], xv[8], d[8], res[8];
+    const int groups = (hw + GPIX - 1) / GPIX;
+    const long long pg = e / c8;
+    const int n = (int)(pg / groups);
+    const int q0 = (int)(pg - (long long)n * groups) * GPIX;
+    float sc[8], sh[8], m[8], r[8], g[8], a1[8], a2[8];
     affine8(mean + (size_t)n * C + cc, rstd + (size_t)n * C + cc, gamma + cc, beta + cc, sc, sh);
     load8f(mean + (size_t)n * C + cc, m);
     load8f(rstd + (size_t)n * C + cc, r);
     load8f(gamma + cc, g);
     load8f(A1 + (size_t)n * C + cc, a1);
     load8f(A2 + (size_t)n * C + cc, a2);
-    load8<T>(x + (size_t)p * C + cc, xv);
-    if (ident) {
-        float up[8];
-        load8<T>(dout + (size_t)p * C + cc, up);
+    const size_t base = (size_t)n * hw * C + cc;
+    float xv[GPIX][8], d[GPIX][8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) d[u] = (fmaf(xv[u], sc[u], sh[u]) > 0.f) ? up[u] : 0.f;
-    } else {
-        load8f(dyh + (size_t)p * C + cc, d);
+    for (int q = 0; q < GPIX; ++q) {
+        if (q0 + q >= hw) continue;
+        load8<T>(x + base + (size_t)(q0 + q) * C, xv[q]);
+        if (ident) load8<T>(dout + base + (size_t)(q0 + q) * C, d[q]);
+        else load8f(dyh + base + (size_t)(q0 + q) * C, d[q]);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const float xh = (xv[u] - m[u]) * r[u];
-        res[u] = r[u] * (g[u] * d[u] - a1[u] - xh * a2[u]);
+    for (int q = 0; q < GPIX; ++q) {
+        if (q0 + q >= hw) break;
+        float res[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float dv = d[q][u];
+            if (ident) dv = (fmaf(xv[q][u], sc[u], sh[u]) > 0.f) ? dv : 0.f;
+            const float xh = (xv[q][u] - m[u]) * r[u];
+            res[u] = r[u] * (g[u] * dv - a1[u] - xh * a2[u]);
+        }
+        store8<T>(dx + base + (size_t)(q0 + q) * C, res);
     }
-    store8<T>(dx + (size_t)p * C + cc, res);
 }
 
 bool gn_shape_ok(int C, int cpg) {
@@ -321,7 +350,7 @@ extern "C" int ge_gn_relu_upsample_fwd(const void* x, const float* mean, const f
     GE_REQUIRE(x && mean && rstd && gamma && beta && out, GE_ERR_ARG, "ge_gn_relu_upsample_fwd: null pointer");
     GE_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0, GE_ERR_ARG, "ge_gn_relu_upsample_fwd: bad dimension");
     GE_REQUIRE(C % 8 == 0, GE_ERR_SHAPE, "ge_gn_relu_upsample_fwd: C=%d must be a multiple of 8", C);
-    const long long total8 = (long long)N * H * W * (C / 8);
+    const long long total8 = (long long)N * ge::cdiv(H * W, GPIX) * (C / 8);
     const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GE_DTYPE_F32)
@@ -348,7 +377,7 @@ extern "C" int ge_gn_relu_upsample_bwd(const void* dout, const void* x, const fl
     GE_REQUIRE(ident || dyh, GE_ERR_ARG, "ge_gn_relu_upsample_bwd: dyh scratch is required for an up-sampling call");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = gn_smem(C);
-    const long long total8 = (long long)N * h * w * (C / 8);
+    const long long total8 = (long long)N * ge::cdiv(h * w, GPIX) * (C / 8);
     const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
     static size_t c0 = 0, c1 = 0;
     if (dtype == GE_DTYPE_F32) {

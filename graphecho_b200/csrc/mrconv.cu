@@ -44,7 +44,9 @@ mrconv_gather_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
     unsigned char* ab = argk + (size_t)b * C * N;
     const int* mynb = nb + threadIdx.x * k;
     const int* myct = ct + threadIdx.x * k;
-    for (int c = 0; c < C; ++c) {
+    const int cper = (C + gridDim.z - 1) / gridDim.z;
+    const int cbeg = blockIdx.z * cper, cend = min(C, cbeg + cper);
+    for (int c = cbeg; c < cend; ++c) {
         const float* xc = xb + (size_t)c * N;
         const float* yc = yb + (size_t)c * M;
         float best = -INFINITY;
@@ -117,7 +119,11 @@ extern "C" int ge_mrconv_gather_fwd(const float* x, const float* y, const long l
     const size_t smem = (size_t)2 * MR_THREADS * k * sizeof(int);
     GE_REQUIRE(smem <= 200 * 1024, GE_ERR_CAPACITY, "ge_mrconv_gather_fwd: k too large");
     { static size_t ge_max_smem__ = 0; if ((size_t)(smem) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(mrconv_gather_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)), "ge_mrconv_gather_fwd(attr)"); ge_max_smem__ = (size_t)(smem); } }
-    mrconv_gather_fwd_kernel<<<dim3(ge::cdiv(N, MR_THREADS), B), MR_THREADS, smem, (cudaStream_t)stream>>>(
+    // channel chunks in grid.z so that small graphs still fill the machine
+    const long long ctas = (long long)ge::cdiv(N, MR_THREADS) * B;
+    int zc = 1;
+    while (zc < 8 && ctas * zc < (long long)ge::sm_count() * 16 && C / (zc * 2) >= 16) zc *= 2;
+    mrconv_gather_fwd_kernel<<<dim3(ge::cdiv(N, MR_THREADS), B, zc), MR_THREADS, smem, (cudaStream_t)stream>>>(
         x, y, idx_nbr, idx_ctr, out, argk, C, N, M, k);
     GE_CHECK_LAUNCH("ge_mrconv_gather_fwd");
     return GE_OK;

@@ -359,14 +359,18 @@ class _GnReluUpsample(Function):
         xc, mean, rstd, g, b = ctx.saved_tensors
         N, C, h, w, H, W, cpg, gdt, bdt = ctx.cfg
         d = _nhwc_view(dout.to(xc.dtype))
-        ident = (h, w) == (H, W)
-        dyh = None if ident else torch.empty((N, h, w, C), device=d.device, dtype=torch.float32)
+        es = xc.element_size()
+        if (h, w) != (H, W):
+            # adjoint of the up-sampling first (the source map is small), then the same-size backward
+            dact = torch.empty_like(xc)
+            call("ge_upsample_bwd", ptr(d), ptr(dact), _dtype_code(d), N, h, w, H, W, C, stream(),
+                 work=(N * C * es * (h * w + H * W), 2 * N * C * H * W))
+            d = dact
         S = torch.empty((4, N, C), device=d.device, dtype=torch.float32)
         dx = torch.empty_like(xc)
-        es = xc.element_size()
-        call("ge_gn_relu_upsample_bwd", ptr(d), ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(dyh),
-             ptr(S[0]), ptr(S[1]), ptr(S[2]), ptr(S[3]), ptr(dx), _dtype_code(xc), N, h, w, H, W, C, cpg, stream(),
-             work=(N * C * (es * (H * W + 3 * h * w) + (0 if ident else 8 * h * w)), 20 * N * C * H * W))
+        call("ge_gn_relu_upsample_bwd", ptr(d), ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(None),
+             ptr(S[0]), ptr(S[1]), ptr(S[2]), ptr(S[3]), ptr(dx), _dtype_code(xc), N, h, w, h, w, C, cpg, stream(),
+             work=(N * C * es * 4 * h * w, 20 * N * C * h * w))
         return dx, S[1].sum(0).to(gdt), S[0].sum(0).to(bdt), None, None, None
 
 

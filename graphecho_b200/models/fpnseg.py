@@ -185,11 +185,17 @@ class FPN(nn.Module):
         hw = q2.shape[-2:]
         g1, g2 = self.gn1, self.gn2
 
+        # GroupNorm(C, C) normalises every channel on its own, so a per-channel constant added before it
+        # cancels exactly: the biases of conv2 / semantic_branch cannot influence the output (their true
+        # gradient is identically zero).  Skipping them saves cuDNN's bias-gradient reductions over the
+        # largest maps of the head; the parameters stay in the state_dict, untouched.
         def wide(t):        # conv2 -> GroupNorm(256,256) -> ReLU -> _upsample      (fpnseg.py:428-435)
-            return GF.gn_relu_upsample(self.conv2(t), g2.weight, g2.bias, hw, g2.eps)
+            y = F.conv2d(t, self.conv2.weight, None, 1, 1)
+            return GF.gn_relu_upsample(y, g2.weight, g2.bias, hw, g2.eps)
 
         def narrow(t):      # semantic_branch -> GroupNorm(128,128) -> ReLU -> _upsample
-            return GF.gn_relu_upsample(self.semantic_branch(t), g1.weight, g1.bias, hw, g1.eps)
+            y = F.conv2d(t, self.semantic_branch.weight, None, 1, 1)
+            return GF.gn_relu_upsample(y, g1.weight, g1.bias, hw, g1.eps)
 
         s5 = narrow(wide(wide(p5)))
         s4 = narrow(wide(q4))

@@ -165,8 +165,9 @@ class DyGraphConv2d(GraphConv2d):
         B, C, H, W = x.shape
         y = None
         if self.r > 1:
-            y = F.avg_pool2d(x, self.r, self.r).reshape(B, C, -1, 1).contiguous()
-        x = x.reshape(B, C, -1, 1).contiguous()
+            y = F.avg_pool2d(x, self.r, self.r).reshape(B, C, -1, 1).float().contiguous()
+        # one fp32 [B,C,N,1] copy feeds both the k-NN build and the max-relative gather
+        x = x.reshape(B, C, -1, 1).float().contiguous()
         edge_index = self.dilated_knn_graph(x, y, relative_pos)
         x = super().forward(x, edge_index, y)
         return x.reshape(B, -1, H, W).contiguous()
