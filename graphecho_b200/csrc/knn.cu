@@ -354,6 +354,154 @@ knn_graph_fast_kernel(const float* __restrict__ x, const float* __restrict__ y,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wide path (K <= 32): 128 queries x 64 keys per CTA step, 8x4 register tiles (3 shared-memory vector
+// loads per 32 FFMA, so the FFMA pipe -- not shared-memory bandwidth -- is the limiter), both operands
+// streamed through a 2-stage cp.async ring in 32-channel chunks, running top-K lists in shared memory
+// (one slot per lane).
+constexpr int WQ = 128;
+constexpr int WXLD = WQ + 4;
+
+struct List1 { float d; int i; };   // sorted ascending, lane l holds slot l
+
+__device__ __forceinline__ void list1_insert(List1& L, float d, int idx, int K, int lane) {
+    const int p = __popc(__ballot_sync(ge::kFull, L.d <= d));
+    if (p >= K) return;
+    const float upd = __shfl_up_sync(ge::kFull, L.d, 1);
+    const int upi = __shfl_up_sync(ge::kFull, L.i, 1);
+    if (lane > p) { L.d = upd; L.i = upi; }
+    else if (lane == p) { L.d = d; L.i = idx; }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_graph_wide_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                      const float* __restrict__ xsq, const float* __restrict__ ysq,
+                      const float* __restrict__ rel, long long* __restrict__ out,
+                      int B, int C, int N, int M, int K, int dilation, int LS) {
+    extern __shared__ __align__(16) float smem[];
+    float* Xb = smem;                              // [2][FKC][WXLD]
+    float* Yb = Xb + 2 * FKC * WXLD;               // [2][FKC][XLD]
+    float* Ds = Yb + 2 * FKC * XLD;                // [WQ][DLD]
+    float* s_xsq = Ds + WQ * DLD;                  // [WQ]
+    float* s_ysq = s_xsq + WQ;                     // [TK]
+    float* Ld = s_ysq + TK;                        // [WQ][LS] list distances (LS = 16 or 32 slots)
+    int* Li = reinterpret_cast<int*>(Ld + WQ * LS);// [WQ][LS] list indices
+
+    const int b = blockIdx.y, i0 = blockIdx.x * WQ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;        // rows ty*8.., cols tx*4..
+    const float* xb = x + (size_t)b * C * N;
+    const float* yb = y + (size_t)b * C * M;
+    const int nchunks = C / FKC;
+    const int ntiles = (M + TK - 1) / TK;
+
+    if (tid < WQ) s_xsq[tid] = (i0 + tid < N) ? xsq[(size_t)b * N + i0 + tid] : 0.f;
+    for (int e = tid; e < WQ * LS; e += KNN_THREADS) { Ld[e] = INFINITY; Li[e] = 0; }
+
+    auto issue = [&](int step) {
+        const int tile = step / nchunks, ch = step - tile * nchunks;
+        const int j0 = tile * TK, c0 = ch * FKC;
+        float* dx = Xb + (step & 1) * FKC * WXLD;
+        float* dy = Yb + (step & 1) * FKC * XLD;
+        for (int e = tid; e < FKC * (WQ / 4); e += KNN_THREADS) {
+            const int kc = e / (WQ / 4), p4 = (e - kc * (WQ / 4)) * 4;
+            cp_async16(dx + kc * WXLD + p4, xb + (size_t)(c0 + kc) * N + i0 + p4, i0 + p4 < N);
+        }
+        for (int e = tid; e < FKC * (TK / 4); e += KNN_THREADS) {
+            const int kc = e / (TK / 4), p4 = (e - kc * (TK / 4)) * 4;
+            cp_async16(dy + kc * XLD + p4, yb + (size_t)(c0 + kc) * M + j0 + p4, j0 + p4 < M);
+        }
+        cp_async_commit();
+    };
+
+    const int nsteps = ntiles * nchunks;
+    issue(0);
+    float acc[8][4];
+    for (int step = 0; step < nsteps; ++step) {
+        const int tile = step / nchunks, ch = step - tile * nchunks;
+        if (ch == 0) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+        }
+        if (step + 1 < nsteps) { issue(step + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        const float* Xc = Xb + (step & 1) * FKC * WXLD + ty * 8;
+        const float* Yc = Yb + (step & 1) * FKC * XLD + tx * 4;
+#pragma unroll 8
+        for (int kc = 0; kc < FKC; ++kc) {
+            const float4 a0 = *reinterpret_cast<const float4*>(Xc + kc * WXLD);
+            const float4 a1 = *reinterpret_cast<const float4*>(Xc + kc * WXLD + 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(Yc + kc * XLD);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+        }
+        if (ch == nchunks - 1) {
+            const int j0 = tile * TK;
+            if (tid < TK) s_ysq[tid] = (j0 + tid < M) ? ysq[(size_t)b * M + j0 + tid] : 0.f;
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int il = ty * 8 + a, jl = tx * 4 + c;
+                    float d = (s_xsq[il] + (-2.f * acc[a][c])) + s_ysq[jl];
+                    const int i = i0 + il, j = j0 + jl;
+                    if (rel != nullptr && i < N && j < M) d += rel[(size_t)i * M + j];
+                    if (j >= M) d = INFINITY;
+                    Ds[il * DLD + jl] = d;
+                }
+            __syncthreads();
+            for (int r = 0; r < WQ / 8; ++r) {      // warp w owns rows 16w .. 16w+15
+                const int il = warp * (WQ / 8) + r;
+                List1 L;
+                L.d = lane < LS ? Ld[il * LS + lane] : INFINITY;
+                L.i = lane < LS ? Li[il * LS + lane] : 0;
+                float thr = __shfl_sync(ge::kFull, L.d, K - 1);
+                bool dirty = false;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float d = Ds[il * DLD + lane + 32 * h];
+                    unsigned pass = __ballot_sync(ge::kFull, d < thr);
+                    while (pass) {
+                        const int src = __ffs(pass) - 1;
+                        pass &= pass - 1;
+                        const float dc = __shfl_sync(ge::kFull, d, src);
+                        if (dc < thr) {
+                            list1_insert(L, dc, j0 + src + 32 * h, K, lane);
+                            thr = __shfl_sync(ge::kFull, L.d, K - 1);
+                            dirty = true;
+                        }
+                    }
+                }
+                if (dirty && lane < LS) { Ld[il * LS + lane] = L.d; Li[il * LS + lane] = L.i; }
+            }
+        }
+        __syncthreads();
+    }
+    const int kout = K / dilation;
+    long long* out0 = out + (size_t)b * N * kout;
+    long long* out1 = out + (size_t)B * N * kout + (size_t)b * N * kout;
+    for (int e = tid; e < WQ * LS; e += KNN_THREADS) {
+        const int il = e / LS, sidx = e - il * LS;
+        const int i = i0 + il;
+        if (i < N && sidx < K && (sidx % dilation) == 0) {
+            const int o = sidx / dilation;
+            out0[(size_t)i * kout + o] = Li[e];
+            out1[(size_t)i * kout + o] = i;
+        }
+    }
+}
+
+size_t knn_wide_smem(int LS) {
+    return ((size_t)2 * FKC * WXLD + 2 * FKC * XLD + WQ * DLD + WQ + TK + 2 * WQ * LS) * sizeof(float);
+}
+
 size_t knn_fast_smem(int C) {
     return ((size_t)C * XLD + 2 * FKC * XLD + TQ * DLD + TQ + TK) * sizeof(float);
 }
@@ -392,7 +540,20 @@ extern "C" int ge_knn_graph(const float* x, const float* y, const float* relativ
     const size_t smem = knn_fast_smem(C);
     const bool fast = (N % 4 == 0) && (M % 4 == 0) && (C % FKC == 0) && smem <= 110 * 1024 &&
                       (reinterpret_cast<uintptr_t>(xn) % 16 == 0);
-    if (fast) {
+    const bool wide = (N % 4 == 0) && (M % 4 == 0) && (C % FKC == 0) && K <= 32 && N >= WQ &&
+                      (reinterpret_cast<uintptr_t>(xn) % 16 == 0);
+    if (wide) {
+        static size_t wcached = 0;
+        const int LS = K <= 16 ? 16 : 32;
+        const size_t wsmem = knn_wide_smem(LS);
+        if (wsmem > wcached) {
+            GE_CUDA(cudaFuncSetAttribute(knn_graph_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem),
+                    "ge_knn_graph(attr)");
+            wcached = wsmem;
+        }
+        knn_graph_wide_kernel<<<dim3(ge::cdiv(N, WQ), B), KNN_THREADS, wsmem, st>>>(xn, yn, xsq, ysq, relative_pos,
+                                                                                    edge_index, B, C, N, M, K, dilation, LS);
+    } else if (fast) {
         static size_t cached = 0;
         if (smem > cached) {
             GE_CUDA(cudaFuncSetAttribute(knn_graph_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

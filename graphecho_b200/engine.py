@@ -217,7 +217,8 @@ class UDAEngine:
         from . import _cabi
         before = _cabi.launch_count()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16, cache_enabled=False):
-            graphed = torch.cuda.make_graphed_callables(tuple(calls), tuple(samples), num_warmup_iters=3)
+            graphed = torch.cuda.make_graphed_callables(tuple(calls), tuple(samples), num_warmup_iters=3,
+                                                        allow_unused_input=True)
         # 3 warm-up executions + 1 capture of every segment's forward and backward
         self.graph_launches = (_cabi.launch_count() - before) // 4
         for name, g in zip(names, graphed):
