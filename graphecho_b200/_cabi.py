@@ -33,6 +33,7 @@ _SIGNATURES = {
     "ge_sinkhorn_rpm_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, P]),
     "ge_sinkhorn_distance_fwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, c_double, P]),
     "ge_sinkhorn_distance_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
+    "ge_knn_graph_set_path": (c_int, [I]),
     "ge_knn_graph_workspace_bytes": (c_size_t, [I, I, I, I]),
     "ge_knn_graph": (c_int, [P, P, P, P, P, Z, I, I, I, I, I, I, P]),
     "ge_mrconv_gather_fwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P]),

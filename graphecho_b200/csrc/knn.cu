@@ -13,6 +13,7 @@
 // distance, every dilation-th entry), [1] = centre index                [vig.py:328-329, 353].
 // Work: 2*B*N*M*C flops; algorithmic bytes 4*B*C*(N+M) + 16*B*N*k.
 #include "common.cuh"
+#include "knn_tc.cuh"
 #include "../../include/graphecho_b200.h"
 
 namespace {
@@ -508,10 +509,22 @@ size_t knn_fast_smem(int C) {
 
 }  // namespace
 
+namespace {
+int g_knn_path = 0;   // 0 = choose, 1 = fp32 FFMA kernels only, 2 = require the tcgen05 kernel
+}
+
+extern "C" int ge_knn_graph_set_path(int path) {
+    GE_REQUIRE(path >= 0 && path <= 2, GE_ERR_ARG, "ge_knn_graph_set_path: path must be 0, 1 or 2");
+    g_knn_path = path;
+    return GE_OK;
+}
+
 extern "C" size_t ge_knn_graph_workspace_bytes(int B, int C, int N, int M) {
     if (B <= 0 || C <= 0 || N <= 0 || M <= 0) return 0;
-    // normalised copies of x and y + their squared norms
-    return ((size_t)B * C * ((size_t)N + M) + (size_t)B * ((size_t)N + M)) * sizeof(float);
+    // FFMA path: normalised copies of x and y + their squared norms; tcgen05 path: K-major TF32 hi/lo splits
+    const size_t ffma = ((size_t)B * C * ((size_t)N + M) + (size_t)B * ((size_t)N + M)) * sizeof(float);
+    const size_t tc = ge::knn_tc_workspace_bytes(B, C, N, M);
+    return ffma > tc ? ffma : tc;
 }
 
 extern "C" int ge_knn_graph(const float* x, const float* y, const float* relative_pos, long long* edge_index,
@@ -525,6 +538,11 @@ extern "C" int ge_knn_graph(const float* x, const float* y, const float* relativ
     GE_REQUIRE(y != nullptr || N == M, GE_ERR_SHAPE, "ge_knn_graph: self-graph needs M == N");
     GE_REQUIRE(workspace_bytes >= ge_knn_graph_workspace_bytes(B, C, N, M), GE_ERR_ARG, "ge_knn_graph: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool tc_ok = ge::knn_tc_applicable(B, C, N, M, K, relative_pos != nullptr) &&
+                       reinterpret_cast<uintptr_t>(workspace) % 128 == 0;
+    GE_REQUIRE(g_knn_path != 2 || tc_ok, GE_ERR_SHAPE,
+               "ge_knn_graph: the tcgen05 path was required but does not cover B=%d C=%d N=%d M=%d K=%d", B, C, N, M, K);
+    if (tc_ok && g_knn_path != 1) return ge::knn_tc_run(x, y, edge_index, workspace, B, C, N, M, K, dilation, st);
     float* xn = static_cast<float*>(workspace);
     float* yn = xn + (size_t)B * C * N;
     float* xsq = yn + (size_t)B * C * M;

@@ -1,0 +1,438 @@
+// K1 on the 5th-generation tensor cores: dense dilated k-NN graph build (ViG Grapher, N >= 128).
+//
+// Same contract as the FFMA kernels in knn.cu (DenseDilatedKnnGraph.forward ->
+// (xy_)dense_knn_matrix -> (xy_)pairwise_distance -> topk, /root/reference/models/vig.py:232-381),
+// but the [N,M] inner-product GEMM -- 2*B*N*M*C flops, the whole cost of the op -- runs on
+// tcgen05.mma (kind::tf32) with the accumulator in TMEM and operands staged by TMA:
+//
+//   * pre-pass (knn_split_kernel): L2-normalise every point (F.normalize, vig.py:372-373), transpose
+//     to K-major [B,N,C] and split each fp32 value into two TF32 terms  v = hi + lo  (hi = v rounded
+//     to 11 significant bits, lo = the exact remainder truncated to TF32).  The inner product is
+//     accumulated as  lo.hi' + hi.lo' + hi.hi'  in fp32 (3xTF32): the dropped lo.lo' term and the
+//     truncation of lo are both <= 2^-23 relative, i.e. fp32-level, so near-ties order like the
+//     fp32 reference (tests accept either order only where two distances differ by < 2e-6).
+//   * main kernel (knn_tc_kernel): one CTA per (batch, 128-query tile).  Warp 0 = TMA producer
+//     (4 SWIZZLE_128B tiles per 32-channel stage: query hi/lo, key hi/lo, 3-stage mbarrier ring),
+//     warp 1 = MMA issuer (one elected thread, 12 tcgen05.mma per stage, accumulator double-buffered
+//     in TMEM so the next key tile's GEMM overlaps the selection of the current one), warps 2-5 =
+//     selection: tcgen05.ld gives every thread ONE query row of the distance tile, so each thread
+//     keeps its own sorted top-K list in registers (no shuffles, no shared memory), forming
+//       dist = (|x^|^2 + (-2 x^.y^)) + |y^|^2                               [vig.py:270-274]
+//     exactly as the reference orders the additions.  Ties -> lower key index.
+//   * output int64 [2,B,N,k]: [0] = neighbour (sorted by distance, every dilation-th entry),
+//     [1] = centre index                                                    [vig.py:328-329, 353].
+//
+// Work: 2*B*N*M*C algorithmic flops (x3 on the tensor pipe); bytes 4*B*C*(N+M) + 16*B*N*k.
+#include "common.cuh"
+#include "knn_tc.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TC_BM = 128;                         // query rows per CTA (UMMA M)
+constexpr int TC_BK = 32;                          // channels per stage = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;   // one [128][32] fp32 operand tile
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // query hi, query lo, key hi, key lo
+constexpr int TC_THREADS = 192;                    // producer warp, MMA warp, 4 selection warps
+constexpr int TC_TMEM_COLS = 256;                  // 2 accumulator buffers x 128 columns
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 bytes apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;   // stride byte offset
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// Pre-pass: normalise, transpose to [B,N,C], split into TF32 hi / lo, squared norms of the fp32
+// normalised vectors.  CTA = 32 points x all channels through a padded shared tile.
+__global__ void __launch_bounds__(256)
+knn_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                 float* __restrict__ sq, int C, int N, int sq_stride) {
+    extern __shared__ float tile[];              // [C][33]
+    const int b = blockIdx.y, n0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* xb = x + (size_t)b * C * N;
+    for (int c = warp; c < C; c += 8) tile[c * 33 + lane] = (n0 + lane < N) ? xb[(size_t)c * N + n0 + lane] : 0.f;
+    __syncthreads();
+    for (int q = 0; q < 4; ++q) {                // warp w owns points 4w .. 4w+3
+        const int p = warp * 4 + q, n = n0 + p;
+        if (n >= N) break;                       // uniform per warp
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) { const float v = tile[c * 33 + p]; s = fmaf(v, v, s); }
+        s = ge::warp_sum(s);
+        const float d = fmaxf(sqrtf(s), 1e-12f);
+        float* oh = hi + ((size_t)b * N + n) * C;
+        float* ol = lo + ((size_t)b * N + n) * C;
+        float qsum = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float v = tile[c * 33 + p] / d;
+            qsum = fmaf(v, v, qsum);
+            const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+            const float l = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
+            oh[c] = h;
+            ol[c] = l;
+        }
+        qsum = ge::warp_sum(qsum);
+        if (lane == 0) sq[(size_t)b * sq_stride + n] = qsum;
+    }
+}
+
+__global__ void knn_fill_pad_kernel(float* __restrict__ sq, int M, int Mpad, int B) {
+    const int per = Mpad - M;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * B) return;
+    const int b = t / per, j = M + (t - b * per);
+    sq[(size_t)b * Mpad + j] = INFINITY;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-thread sorted list (ascending) of KL slots held in registers.  Only the last K slots are live: the
+// first KL-K hold -inf sentinels that nothing can displace, so the admission threshold is always the
+// statically indexed d[KL-1] (a run-time d[K-1] would push the whole list into local memory).
+template <int KL>
+struct RegList {
+    float d[KL];
+    int i[KL];
+    __device__ __forceinline__ void init(int K) {
+#pragma unroll
+        for (int s = 0; s < KL; ++s) { d[s] = (s < KL - K) ? -INFINITY : INFINITY; i[s] = 0; }
+    }
+    __device__ __forceinline__ float thr() const { return d[KL - 1]; }
+    // insert (dist, idx) after every entry <= dist (earlier = lower key index wins ties)
+    __device__ __forceinline__ void insert(float dist, int idx) {
+#pragma unroll
+        for (int s = KL - 1; s > 0; --s) {
+            const bool up = d[s - 1] > dist;
+            const bool put = !up && d[s] > dist;
+            i[s] = up ? i[s - 1] : (put ? idx : i[s]);
+            d[s] = up ? d[s - 1] : (put ? dist : d[s]);
+        }
+        if (d[0] > dist) { d[0] = dist; i[0] = idx; }
+    }
+};
+
+template <int KL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
+              const __grid_constant__ CUtensorMap tm_yh, const __grid_constant__ CUtensorMap tm_yl,
+              const float* __restrict__ xsq, const float* __restrict__ ysq_pad, long long* __restrict__ out,
+              int B, int N, int M, int Mpad, int BN, int nkb, int K, int dilation, int xsq_stride) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;
+    // barriers: full[3], empty[3], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, i0 = blockIdx.x * TC_BM;
+    const int ntiles = Mpad / BN;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xh) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xl) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_yh) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_yl) : "memory");
+            const uint32_t stage_tx = 2u * TC_TILE_BYTES + 2u * (uint32_t)BN * 128u;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), stage_tx);
+                    const uint32_t dst = base + s * TC_STAGE_BYTES;
+                    tma_load_3d(dst, &tm_xh, full_bar(s), kb * TC_BK, i0, b);
+                    tma_load_3d(dst + TC_TILE_BYTES, &tm_xl, full_bar(s), kb * TC_BK, i0, b);
+                    tma_load_3d(dst + 2 * TC_TILE_BYTES, &tm_yh, full_bar(s), kb * TC_BK, t * BN, b);
+                    tma_load_3d(dst + 3 * TC_TILE_BYTES, &tm_yl, full_bar(s), kb * TC_BK, t * BN, b);
+                    if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B TF32, both K-major, N = BN, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const int buf = t & 1;
+                mbar_wait(tempty_bar(buf), (((uint32_t)t >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * 128u;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_h = base + s * TC_STAGE_BYTES, a_l = a_h + TC_TILE_BYTES;
+                    const uint32_t b_h = a_h + 2 * TC_TILE_BYTES, b_l = a_h + 3 * TC_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {            // UMMA_K = 8 TF32 = 32 bytes
+                        const uint64_t dah = tc_smem_desc(a_h + k * 32), dal = tc_smem_desc(a_l + k * 32);
+                        const uint64_t dbh = tc_smem_desc(b_h + k * 32), dbl = tc_smem_desc(b_l + k * 32);
+                        tc_mma_tf32(d_tmem, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
+                        tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                        tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                    tc_commit(empty_bar(s));                        // frees the smem stage when these MMAs retire
+                    if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+                }
+                tc_commit(tfull_bar(buf));                          // accumulator of tile t complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== selection warps: thread <-> one query row of the accumulator =====
+        const int q = warp & 3;                                     // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane, i = i0 + row;
+        const float xs = (i < N) ? xsq[(size_t)b * xsq_stride + i] : 0.f;
+        const float* ysq = ysq_pad + (size_t)b * Mpad;
+        RegList<KL> L;
+        L.init(K);
+        const int nchunks = BN >> 4;
+        for (int t = 0; t < ntiles; ++t) {
+            const int buf = t & 1;
+            mbar_wait(tfull_bar(buf), ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 128u;
+            const int j0 = t * BN;
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t r[16];
+                tc_ld16(taddr + (uint32_t)(c * 16), r);
+                float ys[16];
+                const float4* yp = reinterpret_cast<const float4*>(ysq + j0 + c * 16);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 v = __ldg(yp + e);
+                    ys[4 * e] = v.x; ys[4 * e + 1] = v.y; ys[4 * e + 2] = v.z; ys[4 * e + 3] = v.w;
+                }
+                tc_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float dist = (xs + (-2.f * __uint_as_float(r[e]))) + ys[e];   // padded keys carry +inf
+                    if (dist < L.thr()) L.insert(dist, j0 + c * 16 + e);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+        if (i < N) {
+            const int kout = K / dilation;
+            long long* out0 = out + ((size_t)b * N + i) * kout;
+            long long* out1 = out + (size_t)B * N * kout + ((size_t)b * N + i) * kout;
+#pragma unroll
+            for (int s = 0; s < KL; ++s) {
+                const int o = s - (KL - K);                         // rank among the live slots
+                if (o >= 0 && (o % dilation) == 0) {
+                    out0[o / dilation] = L.i[s];
+                    out1[o / dilation] = i;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [B][rows][C] fp32, box = {32 channels, box_rows, 1}, 128-byte swizzle, out-of-bounds rows read as zero
+bool make_map(CUtensorMap* map, const float* ptr, int B, int rows, int C, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)rows * C * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int pick_bn(int M) {                     // key-tile width (UMMA N): least padding, then widest
+    int best = 128, best_pad = ge::cdiv(M, 128) * 128;
+    for (int bn = 112; bn >= 64; bn -= 16) {
+        const int pad = ge::cdiv(M, bn) * bn;
+        if (pad < best_pad) { best = bn; best_pad = pad; }
+    }
+    return best;
+}
+
+template <int KL>
+int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& yh, const CUtensorMap& yl,
+              const float* xsq, int xsq_stride, const float* ysq, long long* out, int B, int N, int M, int Mpad, int BN,
+              int nkb, int K, int dilation, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        GE_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM),
+                "ge_knn_graph(tc attr)");
+        attr_done = true;
+    }
+    knn_tc_kernel<KL><<<dim3(ge::cdiv(N, TC_BM), B), TC_THREADS, TC_SMEM, st>>>(xh, xl, yh, yl, xsq, ysq, out, B, N, M, Mpad,
+                                                                                BN, nkb, K, dilation, xsq_stride);
+    GE_CHECK_LAUNCH("ge_knn_graph(tcgen05)");
+    return GE_OK;
+}
+
+}  // namespace
+
+namespace ge {
+
+bool knn_tc_applicable(int B, int C, int N, int M, int K, bool has_rel) {
+    return !has_rel && C % TC_BK == 0 && C >= TC_BK && C * 33 * 4 <= 200 * 1024 && K <= 32 && N >= 128 && M >= 128 &&
+           B <= 65535 && encode_fn() != nullptr;
+}
+
+size_t knn_tc_workspace_bytes(int B, int C, int N, int M) {
+    const size_t mpad = (size_t)M + 128;
+    return (2 * (size_t)B * C * ((size_t)N + M) + (size_t)B * N + (size_t)B * mpad) * sizeof(float) + 256;
+}
+
+int knn_tc_run(const float* x, const float* y, long long* edge_index, void* workspace,
+               int B, int C, int N, int M, int K, int dilation, cudaStream_t st) {
+    const int BN = pick_bn(M);
+    const int Mpad = ge::cdiv(M, BN) * BN;
+    float* xh = static_cast<float*>(workspace);
+    float* xl = xh + (size_t)B * N * C;
+    float* yh = xl + (size_t)B * N * C;
+    float* yl = yh + (y ? (size_t)B * M * C : 0);
+    float* ysq = yl + (y ? (size_t)B * M * C : 0);           // [B][Mpad], padded keys = +inf
+    float* xsq = ysq + (size_t)B * Mpad;                     // [B][N]
+    const size_t split_smem = (size_t)C * 33 * sizeof(float);
+    static size_t split_cached = 48 * 1024;
+    if (split_smem > split_cached) {
+        GE_CUDA(cudaFuncSetAttribute(knn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem),
+                "ge_knn_graph(split attr)");
+        split_cached = split_smem;
+    }
+    if (y != nullptr) {
+        knn_split_kernel<<<dim3(ge::cdiv(N, 32), B), 256, split_smem, st>>>(x, xh, xl, xsq, C, N, N);
+        GE_CHECK_LAUNCH("ge_knn_graph(split x)");
+        knn_split_kernel<<<dim3(ge::cdiv(M, 32), B), 256, split_smem, st>>>(y, yh, yl, ysq, C, M, Mpad);
+        GE_CHECK_LAUNCH("ge_knn_graph(split y)");
+    } else {
+        // self-graph: keys are the queries; the padded norm row doubles as the query norms
+        knn_split_kernel<<<dim3(ge::cdiv(N, 32), B), 256, split_smem, st>>>(x, xh, xl, ysq, C, N, Mpad);
+        GE_CHECK_LAUNCH("ge_knn_graph(split x)");
+        yh = xh; yl = xl;
+    }
+    if (Mpad > M) {
+        const int n = (Mpad - M) * B;
+        knn_fill_pad_kernel<<<ge::cdiv(n, 256), 256, 0, st>>>(ysq, M, Mpad, B);
+        GE_CHECK_LAUNCH("ge_knn_graph(pad)");
+    }
+    CUtensorMap mxh, mxl, myh, myl;
+    const bool ok = make_map(&mxh, xh, B, N, C, TC_BM) && make_map(&mxl, xl, B, N, C, TC_BM) &&
+                    make_map(&myh, yh, B, M, C, BN) && make_map(&myl, yl, B, M, C, BN);
+    GE_REQUIRE(ok, GE_ERR_SHAPE, "ge_knn_graph: cuTensorMapEncodeTiled failed (B=%d C=%d N=%d M=%d)", B, C, N, M);
+    const float* xsq_p = (y != nullptr) ? xsq : ysq;
+    const int xs = (y != nullptr) ? N : Mpad;
+    const int nkb = C / TC_BK;
+    if (K <= 9) return launch_tc<9>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
+    if (K <= 18) return launch_tc<18>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
+    return launch_tc<32>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
+}
+
+}  // namespace ge

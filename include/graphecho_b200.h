@@ -91,7 +91,13 @@ int ge_sinkhorn_distance_bwd(const float* x, const float* y, const float* C, con
  * DenseDilatedKnnGraph.forward (models/vig.py:369-381) incl. F.normalize, (xy_)pairwise_distance
  * (:232-274), topk (:306/327), centre index + stack (:308-309/328-329) and the dilation stride
  * (:353).  x [B,C,N], y [B,C,M] or NULL (self graph, M == N), relative_pos [N,M] or NULL,
- * edge_index int64 [2,B,N,k]; k*dilation <= 64 and <= M.  Ties -> lower key index. */
+ * edge_index int64 [2,B,N,k]; k*dilation <= 64 and <= M.  Ties -> lower key index.
+ * Two implementations behind the one entry point: the inner-product GEMM on tcgen05.mma
+ * (3xTF32 split = fp32-level accuracy, TMA-staged operands, accumulator in TMEM, per-thread
+ * top-k; used when relative_pos == NULL, C % 32 == 0, k*dilation <= 32 and N, M >= 128) and
+ * fp32 FFMA kernels for everything else.  ge_knn_graph_set_path: 0 = choose (default),
+ * 1 = FFMA kernels only, 2 = require the tcgen05 kernel (GE_ERR_SHAPE if it does not apply). */
+int ge_knn_graph_set_path(int path);
 size_t ge_knn_graph_workspace_bytes(int B, int C, int N, int M);
 int ge_knn_graph(const float* x, const float* y, const float* relative_pos, long long* edge_index,
                  void* workspace, size_t workspace_bytes,
