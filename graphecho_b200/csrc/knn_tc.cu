@@ -34,7 +34,8 @@ constexpr int TC_BK = 32;                          // channels per stage = one 1
 constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;   // one [128][32] fp32 operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // query hi, query lo, key hi, key lo
-constexpr int TC_THREADS = 192;                    // producer warp, MMA warp, 4 selection warps
+// threads = producer warp + MMA warp + 4 x SPLIT selection warps (SPLIT warps share each TMEM lane quarter)
+constexpr int tc_threads(int split) { return 64 + 128 * split; }
 constexpr int TC_TMEM_COLS = 256;                  // 2 accumulator buffers x 128 columns
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
@@ -167,10 +168,33 @@ struct RegList {
         }
         if (d[0] > dist) { d[0] = dist; i[0] = idx; }
     }
+    // merge variant: order by (dist, idx) so that equal distances keep the lower key index first
+    __device__ __forceinline__ void insert_lex(float dist, int idx) {
+#pragma unroll
+        for (int s = KL - 1; s > 0; --s) {
+            const bool up = d[s - 1] > dist || (d[s - 1] == dist && i[s - 1] > idx);
+            const bool put = !up && (d[s] > dist || (d[s] == dist && i[s] > idx));
+            i[s] = up ? i[s - 1] : (put ? idx : i[s]);
+            d[s] = up ? d[s - 1] : (put ? dist : d[s]);
+        }
+        if (d[0] > dist || (d[0] == dist && i[0] > idx)) { d[0] = dist; i[0] = idx; }
+    }
 };
 
-template <int KL>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// dist[e] for a lane-dependent e without dynamic register indexing (binary select tree)
+__device__ __forceinline__ float select16(const float (&v)[16], int e) {
+    const bool b0 = e & 1, b1 = e & 2, b2 = e & 4, b3 = e & 8;
+    float a[8], c[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = b0 ? v[2 * k + 1] : v[2 * k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = b1 ? a[2 * k + 1] : a[2 * k];
+    const float g0 = b2 ? c[1] : c[0], g1 = b2 ? c[3] : c[2];
+    return b3 ? g1 : g0;
+}
+
+template <int KL, int TC_SPLIT>
+__global__ void __launch_bounds__(tc_threads(TC_SPLIT), 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
               const __grid_constant__ CUtensorMap tm_yh, const __grid_constant__ CUtensorMap tm_yl,
               const float* __restrict__ xsq, const float* __restrict__ ysq_pad, long long* __restrict__ out,
@@ -192,7 +216,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * TC_SPLIT); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -204,6 +228,15 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+
+    // selection-warp state lives at function scope: the lists are merged after the role branches join
+    const int q = warp & 3;                                         // TMEM lane quarter this warp may read
+    const int split = (warp >= 2) ? (warp - 2) >> 2 : 0;
+    const int row = q * 32 + lane, i = i0 + row;
+    const float xs = (warp >= 2 && i < N) ? xsq[(size_t)b * xsq_stride + i] : 0.f;
+    const float* ysq = ysq_pad + (size_t)b * Mpad;
+    RegList<KL> L;
+    L.init(K);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -262,13 +295,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
         }
         __syncwarp();
     } else {
-        // ===== selection warps: thread <-> one query row of the accumulator =====
-        const int q = warp & 3;                                     // TMEM lane quarter this warp may read
-        const int row = q * 32 + lane, i = i0 + row;
-        const float xs = (i < N) ? xsq[(size_t)b * xsq_stride + i] : 0.f;
-        const float* ysq = ysq_pad + (size_t)b * Mpad;
-        RegList<KL> L;
-        L.init(K);
+        // ===== selection warps: thread <-> one query row of the accumulator; the TC_SPLIT warps of a
+        // lane quarter take alternating 16-column chunks and keep separate lists, merged at the end =====
         const int nchunks = BN >> 4;
         for (int t = 0; t < ntiles; ++t) {
             const int buf = t & 1;
@@ -276,26 +304,61 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 128u;
             const int j0 = t * BN;
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = (split + t) % TC_SPLIT; c < nchunks; c += TC_SPLIT) {
                 uint32_t r[16];
                 tc_ld16(taddr + (uint32_t)(c * 16), r);
-                float ys[16];
+                float dist[16];
                 const float4* yp = reinterpret_cast<const float4*>(ysq + j0 + c * 16);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float4 v = __ldg(yp + e);
-                    ys[4 * e] = v.x; ys[4 * e + 1] = v.y; ys[4 * e + 2] = v.z; ys[4 * e + 3] = v.w;
+                    dist[4 * e] = v.x; dist[4 * e + 1] = v.y; dist[4 * e + 2] = v.z; dist[4 * e + 3] = v.w;
                 }
                 tc_ld_wait();
+                const float thr0 = L.thr();
+                unsigned mask = 0;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const float dist = (xs + (-2.f * __uint_as_float(r[e]))) + ys[e];   // padded keys carry +inf
-                    if (dist < L.thr()) L.insert(dist, j0 + c * 16 + e);
+                    dist[e] = (xs + (-2.f * __uint_as_float(r[e]))) + dist[e];          // padded keys carry +inf
+                    mask |= (dist[e] < thr0) ? (1u << e) : 0u;
+                }
+                // every lane inserts ITS OWN next candidate per round: rounds = max candidates of a lane,
+                // not the number of columns in which some lane has one
+                while (__any_sync(ge::kFull, mask != 0u)) {
+                    if (mask != 0u) {
+                        const int e = __ffs(mask) - 1;
+                        mask &= mask - 1u;
+                        const float v = select16(dist, e);
+                        if (v < L.thr()) L.insert(v, j0 + c * 16 + e);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();                     // all MMAs retired (every tile was consumed): the stage buffers are free
+    // merge the TC_SPLIT partial lists of every row through shared memory ([split-1][slot][row], conflict-free)
+    float* md = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
+    int* mi = reinterpret_cast<int*>(md + (TC_SPLIT - 1) * KL * TC_BM);
+    if (warp >= 2 && split > 0) {
+#pragma unroll
+        for (int s = 0; s < KL; ++s) {
+            md[((split - 1) * KL + s) * TC_BM + row] = L.d[s];
+            mi[((split - 1) * KL + s) * TC_BM + row] = L.i[s];
+        }
+    }
+    __syncthreads();
+    if (warp >= 2 && split == 0) {
+        for (int o = 0; o < TC_SPLIT - 1; ++o) {
+#pragma unroll
+            for (int s = 0; s < KL; ++s) {
+                const float dv = md[(o * KL + s) * TC_BM + row];
+                const int iv = mi[(o * KL + s) * TC_BM + row];
+                if (dv > -INFINITY && dv <= L.thr()) L.insert_lex(dv, iv);
+            }
         }
         if (i < N) {
             const int kout = K / dilation;
@@ -311,8 +374,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
             }
         }
     }
-    tc_fence_before();
-    __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
@@ -360,17 +421,17 @@ int pick_bn(int M) {                     // key-tile width (UMMA N): least paddi
     return best;
 }
 
-template <int KL>
+template <int KL, int SPLIT>
 int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& yh, const CUtensorMap& yl,
               const float* xsq, int xsq_stride, const float* ysq, long long* out, int B, int N, int M, int Mpad, int BN,
               int nkb, int K, int dilation, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        GE_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM),
+        GE_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KL, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM),
                 "ge_knn_graph(tc attr)");
         attr_done = true;
     }
-    knn_tc_kernel<KL><<<dim3(ge::cdiv(N, TC_BM), B), TC_THREADS, TC_SMEM, st>>>(xh, xl, yh, yl, xsq, ysq, out, B, N, M, Mpad,
+    knn_tc_kernel<KL, SPLIT><<<dim3(ge::cdiv(N, TC_BM), B), tc_threads(SPLIT), TC_SMEM, st>>>(xh, xl, yh, yl, xsq, ysq, out, B, N, M, Mpad,
                                                                                 BN, nkb, K, dilation, xsq_stride);
     GE_CHECK_LAUNCH("ge_knn_graph(tcgen05)");
     return GE_OK;
@@ -430,9 +491,9 @@ int knn_tc_run(const float* x, const float* y, long long* edge_index, void* work
     const float* xsq_p = (y != nullptr) ? xsq : ysq;
     const int xs = (y != nullptr) ? N : Mpad;
     const int nkb = C / TC_BK;
-    if (K <= 9) return launch_tc<9>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
-    if (K <= 18) return launch_tc<18>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
-    return launch_tc<32>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
+    if (K <= 9) return launch_tc<9, 4>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
+    if (K <= 18) return launch_tc<18, 4>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
+    return launch_tc<32, 2>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
 }
 
 }  // namespace ge
