@@ -3,22 +3,27 @@
 // Same contract as the FFMA kernels in knn.cu (DenseDilatedKnnGraph.forward ->
 // (xy_)dense_knn_matrix -> (xy_)pairwise_distance -> topk, /root/reference/models/vig.py:232-381),
 // but the [N,M] inner-product GEMM -- 2*B*N*M*C flops, the whole cost of the op -- runs on
-// tcgen05.mma (kind::tf32) with the accumulator in TMEM and operands staged by TMA:
+// tcgen05.mma (kind::f16) with the accumulators in TMEM and operands staged by TMA:
 //
 //   * pre-pass (knn_split_kernel): L2-normalise every point (F.normalize, vig.py:372-373), transpose
-//     to K-major [B,N,C] and split each fp32 value into two TF32 terms  v = hi + lo  (hi = v rounded
-//     to 11 significant bits, lo = the exact remainder truncated to TF32).  The inner product is
-//     accumulated as  lo.hi' + hi.lo' + hi.hi'  in fp32 (3xTF32): the dropped lo.lo' term and the
-//     truncation of lo are both <= 2^-23 relative, i.e. fp32-level, so near-ties order like the
-//     fp32 reference (tests accept either order only where two distances differ by < 2e-6).
-//   * main kernel (knn_tc_kernel): one CTA per (batch, 128-query tile).  Warp 0 = TMA producer
-//     (4 SWIZZLE_128B tiles per 32-channel stage: query hi/lo, key hi/lo, 3-stage mbarrier ring),
-//     warp 1 = MMA issuer (one elected thread, 12 tcgen05.mma per stage, accumulator double-buffered
-//     in TMEM so the next key tile's GEMM overlaps the selection of the current one), warps 2-5 =
-//     selection: tcgen05.ld gives every thread ONE query row of the distance tile, so each thread
-//     keeps its own sorted top-K list in registers (no shuffles, no shared memory), forming
+//     to K-major [B,N,C] and split each fp32 value v (|v| <= 1) into two fp16 terms
+//         hi = fp16(v),   lo = fp16((v - hi) * 2^11)          =>  v = hi + lo * 2^-11  (+- 2^-22 |v|)
+//     The inner product is accumulated in fp32 in TWO TMEM accumulators,
+//         D1 = sum hi.hi'      D2 = sum (lo.hi' + hi.lo')      x.y = D1 + 2^-11 * D2,
+//     (products of fp16 values are exact in fp32); the dropped lo.lo' term and the rounding of lo are
+//     both ~2^-22 relative, i.e. fp32-level, so near-ties order like the fp32 reference (tests accept
+//     either order only where two distances differ by < 2e-6).  Half the operand bytes and twice the
+//     tensor rate of a 3xTF32 split at the same accuracy.
+//   * main kernel (knn_tc_kernel): one CTA per (batch, 128-query tile).  The query tile (hi and lo,
+//     <= 128 KB) is loaded ONCE by TMA and stays resident in shared memory; key tiles (hi, lo) stream
+//     through a 3-stage mbarrier ring in 64-channel (128-byte, SWIZZLE_128B) slabs.  Warp 0 = TMA
+//     producer, warp 1 = MMA issuer (one elected thread, 12 tcgen05.mma per slab), accumulators
+//     double-buffered in TMEM (2 x 2 x 128 columns) so the next key tile's GEMM overlaps the selection
+//     of the current one.  Warps 2.. = selection: tcgen05.ld gives every thread ONE query row of the
+//     distance tile, so each thread keeps its own sorted top-K list in registers, forming
 //       dist = (|x^|^2 + (-2 x^.y^)) + |y^|^2                               [vig.py:270-274]
-//     exactly as the reference orders the additions.  Ties -> lower key index.
+//     exactly as the reference orders the additions.  SPLIT warps share a row (alternating 16-column
+//     chunks) and their lists are merged through shared memory at the end.  Ties -> lower key index.
 //   * output int64 [2,B,N,k]: [0] = neighbour (sorted by distance, every dilation-th entry),
 //     [1] = centre index                                                    [vig.py:328-329, 353].
 //
@@ -26,18 +31,21 @@
 #include "common.cuh"
 #include "knn_tc.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace {
 
 constexpr int TC_BM = 128;                         // query rows per CTA (UMMA M)
-constexpr int TC_BK = 32;                          // channels per stage = one 128-byte swizzle row
+constexpr int TC_BK = 64;                          // channels per slab = one 128-byte swizzle row of fp16
 constexpr int TC_STAGES = 3;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;   // one [128][32] fp32 operand tile
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // query hi, query lo, key hi, key lo
+constexpr int TC_MAXKB = 4;                        // resident query tile: up to 4 slabs (C <= 256)
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 2;   // one [128][64] fp16 operand slab = 16 KB
+constexpr int TC_A_BYTES = 2 * TC_MAXKB * TC_TILE_BYTES;   // resident query hi + lo
+constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;  // key hi, key lo
+constexpr int TC_TMEM_COLS = 512;                  // 2 buffers x (D1, D2) x 128 columns
+constexpr size_t TC_SMEM = (size_t)TC_A_BYTES + (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 1024 /*key norms*/;
 // threads = producer warp + MMA warp + 4 x SPLIT selection warps (SPLIT warps share each TMEM lane quarter)
 constexpr int tc_threads(int split) { return 64 + 128 * split; }
-constexpr int TC_TMEM_COLS = 256;                  // 2 accumulator buffers x 128 columns
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,12 +81,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -99,13 +107,20 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// one lane of a converged warp (the others skip); keeps the surrounding control flow warp-uniform so the
+// descriptors stay in uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
-// Pre-pass: normalise, transpose to [B,N,C], split into TF32 hi / lo, squared norms of the fp32
+// Pre-pass: normalise, transpose to [B,N,C], split into fp16 hi / scaled lo, squared norms of the fp32
 // normalised vectors.  CTA = 32 points x all channels through a padded shared tile.
 __global__ void __launch_bounds__(256)
-knn_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+knn_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
                  float* __restrict__ sq, int C, int N, int sq_stride) {
     extern __shared__ float tile[];              // [C][33]
     const int b = blockIdx.y, n0 = blockIdx.x * 32;
@@ -120,16 +135,17 @@ knn_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __r
         for (int c = lane; c < C; c += 32) { const float v = tile[c * 33 + p]; s = fmaf(v, v, s); }
         s = ge::warp_sum(s);
         const float d = fmaxf(sqrtf(s), 1e-12f);
-        float* oh = hi + ((size_t)b * N + n) * C;
-        float* ol = lo + ((size_t)b * N + n) * C;
+        __half2* oh = reinterpret_cast<__half2*>(hi + ((size_t)b * N + n) * C);
+        __half2* ol = reinterpret_cast<__half2*>(lo + ((size_t)b * N + n) * C);
         float qsum = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float v = tile[c * 33 + p] / d;
-            qsum = fmaf(v, v, qsum);
-            const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-            const float l = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
-            oh[c] = h;
-            ol[c] = l;
+        for (int c2 = lane; c2 < C / 2; c2 += 32) {          // two adjacent channels per lane
+            const float v0 = tile[(2 * c2) * 33 + p] / d, v1 = tile[(2 * c2 + 1) * 33 + p] / d;
+            qsum = fmaf(v0, v0, qsum);
+            qsum = fmaf(v1, v1, qsum);
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const float r0 = (v0 - __half2float(h0)) * 2048.f, r1 = (v1 - __half2float(h1)) * 2048.f;
+            oh[c2] = __halves2half2(h0, h1);
+            ol[c2] = __halves2half2(__float2half_rn(r0), __float2half_rn(r1));
         }
         qsum = ge::warp_sum(qsum);
         if (lane == 0) sq[(size_t)b * sq_stride + n] = qsum;
@@ -201,14 +217,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
               int B, int N, int M, int Mpad, int BN, int nkb, int K, int dilation, int xsq_stride) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;
-    // barriers: full[3], empty[3], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
+    const uint32_t stage_base = base + TC_A_BYTES;                       // [0, TC_A_BYTES): resident query slabs (hi 0..3, lo 4..7)
+    const uint32_t bar_base = stage_base + TC_STAGES * TC_STAGE_BYTES;
+    // barriers: full[3], empty[3], tmem_full[2], tmem_empty[2], a_full; then the TMEM base address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+    const uint32_t afull_bar = bar_base + 8u * (2 * TC_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 5);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* ys_s = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // [2][128] key norms of the live tiles
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, i0 = blockIdx.x * TC_BM;
@@ -217,6 +236,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * TC_SPLIT); }
+        mbar_init(afull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -233,85 +253,105 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
     const int q = warp & 3;                                         // TMEM lane quarter this warp may read
     const int split = (warp >= 2) ? (warp - 2) >> 2 : 0;
     const int row = q * 32 + lane, i = i0 + row;
-    const float xs = (warp >= 2 && i < N) ? xsq[(size_t)b * xsq_stride + i] : 0.f;
+    const float xs = (warp >= 2 && i < N) ? xsq[(size_t)b * xsq_stride + i] : INFINITY;   // rows past N never admit a key
     const float* ysq = ysq_pad + (size_t)b * Mpad;
     RegList<KL> L;
     L.init(K);
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (whole warp runs the loop, one elected lane issues) =====
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xh) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xl) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_yh) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_yl) : "memory");
-            const uint32_t stage_tx = 2u * TC_TILE_BYTES + 2u * (uint32_t)BN * 128u;
-            int s = 0;
-            uint32_t ph = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), stage_tx);
-                    const uint32_t dst = base + s * TC_STAGE_BYTES;
-                    tma_load_3d(dst, &tm_xh, full_bar(s), kb * TC_BK, i0, b);
-                    tma_load_3d(dst + TC_TILE_BYTES, &tm_xl, full_bar(s), kb * TC_BK, i0, b);
-                    tma_load_3d(dst + 2 * TC_TILE_BYTES, &tm_yh, full_bar(s), kb * TC_BK, t * BN, b);
-                    tma_load_3d(dst + 3 * TC_TILE_BYTES, &tm_yl, full_bar(s), kb * TC_BK, t * BN, b);
-                    if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
-                }
+            // resident query tile: nkb slabs of hi and of lo, one barrier
+            mbar_expect_tx(afull_bar, 2u * (uint32_t)nkb * TC_TILE_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) {
+                tma_load_3d(base + kb * TC_TILE_BYTES, &tm_xh, afull_bar, kb * TC_BK, i0, b);
+                tma_load_3d(base + (TC_MAXKB + kb) * TC_TILE_BYTES, &tm_xl, afull_bar, kb * TC_BK, i0, b);
             }
         }
         __syncwarp();
+        const uint32_t half_tx = (uint32_t)BN * 128u;                 // key hi slab; the lo slab follows it contiguously
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(full_bar(s), 2u * half_tx);
+                    const uint32_t dst = stage_base + s * TC_STAGE_BYTES;
+                    tma_load_3d(dst, &tm_yh, full_bar(s), kb * TC_BK, t * BN, b);
+                    tma_load_3d(dst + half_tx, &tm_yl, full_bar(s), kb * TC_BK, t * BN, b);
+                }
+                __syncwarp();
+                if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            // instruction descriptor: D fp32, A/B TF32, both K-major, N = BN, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const int buf = t & 1;
-                mbar_wait(tempty_bar(buf), (((uint32_t)t >> 1) & 1u) ^ 1u);
+        // ===== MMA issuer (whole warp runs the loop, one elected lane issues) =====
+        // Per 16-channel step two MMAs instead of three: the key hi and lo slabs are contiguous, so
+        //   [D1 | D2] += A_hi . [B_hi ; B_lo]^T   (N = 2*BN)        D2 += A_lo . B_hi^T   (N = BN)
+        // instruction descriptors: D fp32, A/B fp16, both K-major, M = 128
+        const uint32_t idesc_n = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        mbar_wait(afull_bar, 0u);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int buf = t & 1;
+            mbar_wait(tempty_bar(buf), (((uint32_t)t >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d1 = tmem_base + (uint32_t)buf * 256u, d2 = d1 + (uint32_t)BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar(s), ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * 128u;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(full_bar(s), ph);
-                    tc_fence_after();
-                    const uint32_t a_h = base + s * TC_STAGE_BYTES, a_l = a_h + TC_TILE_BYTES;
-                    const uint32_t b_h = a_h + 2 * TC_TILE_BYTES, b_l = a_h + 3 * TC_TILE_BYTES;
+                const uint32_t a_h = base + kb * TC_TILE_BYTES, a_l = base + (TC_MAXKB + kb) * TC_TILE_BYTES;
+                const uint32_t b_h = stage_base + s * TC_STAGE_BYTES;
+                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {            // UMMA_K = 8 TF32 = 32 bytes
+                    for (int k = 0; k < TC_BK / 16; ++k) {           // UMMA_K = 16 fp16 = 32 bytes
                         const uint64_t dah = tc_smem_desc(a_h + k * 32), dal = tc_smem_desc(a_l + k * 32);
-                        const uint64_t dbh = tc_smem_desc(b_h + k * 32), dbl = tc_smem_desc(b_l + k * 32);
-                        tc_mma_tf32(d_tmem, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
-                        tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                        tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                        const uint64_t dbh = tc_smem_desc(b_h + k * 32);
+                        tc_mma_f16(d1, dah, dbh, idesc_2n, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_f16(d2, dal, dbh, idesc_n, 1u);
                     }
                     tc_commit(empty_bar(s));                        // frees the smem stage when these MMAs retire
-                    if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+                    if (kb == nkb - 1) tc_commit(tfull_bar(buf));   // accumulators of tile t complete
                 }
-                tc_commit(tfull_bar(buf));                          // accumulator of tile t complete
+                __syncwarp();
+                if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
             }
         }
-        __syncwarp();
     } else {
         // ===== selection warps: thread <-> one query row of the accumulator; the TC_SPLIT warps of a
         // lane quarter take alternating 16-column chunks and keep separate lists, merged at the end =====
         const int nchunks = BN >> 4;
+        const int sel_tid = tid - 64;                               // 0 .. 128*TC_SPLIT-1
+        float ynext = (sel_tid < BN) ? ysq[sel_tid] : 0.f;          // |y^|^2 of key tile 0 (one key per thread)
         for (int t = 0; t < ntiles; ++t) {
             const int buf = t & 1;
+            const int j0 = t * BN;
+            // stage this tile's key norms in shared memory (double-buffered), prefetch the next tile's
+            if (sel_tid < BN) ys_s[buf * 128 + sel_tid] = ynext;
+            asm volatile("bar.sync 1, %0;" ::"r"(128 * TC_SPLIT) : "memory");
+            if (sel_tid < BN && t + 1 < ntiles) ynext = ysq[j0 + BN + sel_tid];
             mbar_wait(tfull_bar(buf), ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 128u;
-            const int j0 = t * BN;
-            for (int c = (split + t) % TC_SPLIT; c < nchunks; c += TC_SPLIT) {
-                uint32_t r[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 256u;
+            uint32_t r[16], r2[16];
+            int c = (split + t) % TC_SPLIT;
+            if (c < nchunks) {
                 tc_ld16(taddr + (uint32_t)(c * 16), r);
+                tc_ld16(taddr + (uint32_t)BN + (uint32_t)(c * 16), r2);
+            }
+            while (c < nchunks) {
                 float dist[16];
-                const float4* yp = reinterpret_cast<const float4*>(ysq + j0 + c * 16);
+                const float4* yp = reinterpret_cast<const float4*>(ys_s + buf * 128 + c * 16);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float4 v = __ldg(yp + e);
+                    const float4 v = yp[e];
                     dist[4 * e] = v.x; dist[4 * e + 1] = v.y; dist[4 * e + 2] = v.z; dist[4 * e + 3] = v.w;
                 }
                 tc_ld_wait();
@@ -319,19 +359,26 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
                 unsigned mask = 0;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    dist[e] = (xs + (-2.f * __uint_as_float(r[e]))) + dist[e];          // padded keys carry +inf
+                    const float ip = fmaf(__uint_as_float(r2[e]), 1.f / 2048.f, __uint_as_float(r[e]));
+                    dist[e] = (xs + (-2.f * ip)) + dist[e];                              // padded keys carry +inf
                     mask |= (dist[e] < thr0) ? (1u << e) : 0u;
                 }
-                // every lane inserts ITS OWN next candidate per round: rounds = max candidates of a lane,
-                // not the number of columns in which some lane has one
-                while (__any_sync(ge::kFull, mask != 0u)) {
-                    if (mask != 0u) {
-                        const int e = __ffs(mask) - 1;
-                        mask &= mask - 1u;
-                        const float v = select16(dist, e);
-                        if (v < L.thr()) L.insert(v, j0 + c * 16 + e);
-                    }
+                const int cn = c + TC_SPLIT;
+                if (cn < nchunks) {                                  // next chunk's accumulators fly while this one is selected
+                    tc_ld16(taddr + (uint32_t)(cn * 16), r);
+                    tc_ld16(taddr + (uint32_t)BN + (uint32_t)(cn * 16), r2);
                 }
+                // Every lane inserts ITS OWN next candidate per round (rounds = the largest candidate count of a
+                // lane, not the number of columns in which some lane has one).  The round is branch-free and
+                // warp-uniform: a lane without a candidate inserts +inf, which changes nothing.
+                const int rounds = __reduce_max_sync(ge::kFull, __popc(mask));
+                for (int rd = 0; rd < rounds; ++rd) {
+                    const int e = __ffs(mask) - 1;
+                    const float v = (mask != 0u) ? select16(dist, e & 15) : INFINITY;
+                    mask &= mask - 1u;
+                    L.insert(v, j0 + c * 16 + e);
+                }
+                c = cn;
             }
             tc_fence_before();
             __syncwarp();
@@ -399,15 +446,15 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// [B][rows][C] fp32, box = {32 channels, box_rows, 1}, 128-byte swizzle, out-of-bounds rows read as zero
-bool make_map(CUtensorMap* map, const float* ptr, int B, int rows, int C, int box_rows) {
+// [B][rows][C] fp16, box = {64 channels, box_rows, 1}, 128-byte swizzle, out-of-bounds rows / channels read as zero
+bool make_map(CUtensorMap* map, const __half* ptr, int B, int rows, int C, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)rows * C * 4};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows * C * 2};
     const cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(ptr), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -442,24 +489,24 @@ int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& y
 namespace ge {
 
 bool knn_tc_applicable(int B, int C, int N, int M, int K, bool has_rel) {
-    return !has_rel && C % TC_BK == 0 && C >= TC_BK && C * 33 * 4 <= 200 * 1024 && K <= 32 && N >= 128 && M >= 128 &&
-           B <= 65535 && encode_fn() != nullptr;
+    return !has_rel && C % 32 == 0 && C <= TC_MAXKB * TC_BK && K <= 32 && N >= 128 && M >= 128 && B <= 65535 &&
+           encode_fn() != nullptr;
 }
 
 size_t knn_tc_workspace_bytes(int B, int C, int N, int M) {
     const size_t mpad = (size_t)M + 128;
-    return (2 * (size_t)B * C * ((size_t)N + M) + (size_t)B * N + (size_t)B * mpad) * sizeof(float) + 256;
+    return 2 * (size_t)B * C * ((size_t)N + M) * sizeof(__half) + ((size_t)B * N + (size_t)B * mpad) * sizeof(float) + 256;
 }
 
 int knn_tc_run(const float* x, const float* y, long long* edge_index, void* workspace,
                int B, int C, int N, int M, int K, int dilation, cudaStream_t st) {
     const int BN = pick_bn(M);
     const int Mpad = ge::cdiv(M, BN) * BN;
-    float* xh = static_cast<float*>(workspace);
-    float* xl = xh + (size_t)B * N * C;
-    float* yh = xl + (size_t)B * N * C;
-    float* yl = yh + (y ? (size_t)B * M * C : 0);
-    float* ysq = yl + (y ? (size_t)B * M * C : 0);           // [B][Mpad], padded keys = +inf
+    __half* xh = static_cast<__half*>(workspace);
+    __half* xl = xh + (size_t)B * N * C;
+    __half* yh = xl + (size_t)B * N * C;
+    __half* yl = yh + (y ? (size_t)B * M * C : 0);
+    float* ysq = reinterpret_cast<float*>(yl + (y ? (size_t)B * M * C : 0));   // [B][Mpad], padded keys = +inf
     float* xsq = ysq + (size_t)B * Mpad;                     // [B][N]
     const size_t split_smem = (size_t)C * 33 * sizeof(float);
     static size_t split_cached = 48 * 1024;
@@ -490,9 +537,9 @@ int knn_tc_run(const float* x, const float* y, long long* edge_index, void* work
     GE_REQUIRE(ok, GE_ERR_SHAPE, "ge_knn_graph: cuTensorMapEncodeTiled failed (B=%d C=%d N=%d M=%d)", B, C, N, M);
     const float* xsq_p = (y != nullptr) ? xsq : ysq;
     const int xs = (y != nullptr) ? N : Mpad;
-    const int nkb = C / TC_BK;
-    if (K <= 9) return launch_tc<9, 4>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
-    if (K <= 18) return launch_tc<18, 4>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
+    const int nkb = ge::cdiv(C, TC_BK);
+    if (K <= 9) return launch_tc<9, 2>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
+    if (K <= 18) return launch_tc<18, 2>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
     return launch_tc<32, 2>(mxh, mxl, myh, myl, xsq_p, xs, ysq, edge_index, B, N, M, Mpad, BN, nkb, K, dilation, st);
 }
 

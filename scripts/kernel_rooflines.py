@@ -81,11 +81,27 @@ def bench_sinkhorn():
         rows[-1]["sinkhorn_iters_per_s"] = round(5 * B / (ms / 1e3))
 
 
+TENSOR = peaks.get("bf16_tflops", 1590.0) * 1e3   # GFLOP/s, dense 16-bit tensor peak (cuBLAS burst)
+
+
 def bench_knn():
+    lib = _cabi.lib()
     for B, C, N, k in ((8, 256, 64, 9), (256, 256, 784, 9), (16, 256, 4096, 9)):
         x = torch.randn(B, C, N, 1, device=dev)
-        ms = timed(lambda: GF.knn_graph(x, None, k, 1), iters=10)
-        report("ge_knn_graph", f"B{B} C{C} N{N} k{k}", ms, 8 * B * C * N + 16 * B * N * k, 2 * B * N * N * C, "fp32")
+        for path, label in ((1, "ge_knn_graph[fp32 FFMA]"), (0, "ge_knn_graph[tcgen05 2xfp16-split]")):
+            if path == 0 and N < 128:
+                continue
+            lib.ge_knn_graph_set_path(path)
+            ms = timed(lambda: GF.knn_graph(x, None, k, 1), iters=10)
+            lib.ge_knn_graph_set_path(0)
+            flops = 2 * B * N * N * C
+            if path == 1:
+                report(label, f"B{B} C{C} N{N} k{k}", ms, 8 * B * C * N + 16 * B * N * k, flops, "fp32")
+            else:   # tensor roofline: the split issues 3x the algorithmic flops on the 16-bit tensor pipe
+                rows.append(dict(kernel=label, shape=f"B{B} C{C} N{N} k{k}", ms=round(ms, 4),
+                                 GBps=round((8 * B * C * N + 16 * B * N * k) / ms / 1e6, 1), GFLOPs=round(flops / ms / 1e6, 1),
+                                 bound="tensor(3x)", frac=round(3 * flops / ms / 1e6 / TENSOR, 3)))
+                print(json.dumps(rows[-1]), flush=True)
         e = GF.knn_graph(x, None, k, 1)
         ms = timed(lambda: GF.mr_gather(x, e, None), iters=10)
         report("ge_mrconv_gather_fwd", f"B{B} C{C} N{N} k{k}", ms, 4 * B * C * N + 8 * B * N * k + 9 * B * C * N, 2 * B * C * N * k, "hbm")

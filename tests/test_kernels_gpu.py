@@ -195,6 +195,46 @@ def test_knn_all_ties_zero_hidden(dev):
     assert torch.equal(e[0], torch.arange(9).expand(2, 64, 9))
 
 
+def _knn_with_path(path, *args):
+    from graphecho_b200 import _cabi
+    assert _cabi.lib().ge_knn_graph_set_path(path) == 0
+    try:
+        return GF.knn_graph(*args)
+    finally:
+        _cabi.lib().ge_knn_graph_set_path(0)
+
+
+@pytest.mark.parametrize("B,C,N,M,k,d,self_graph", [
+    (1, 32, 128, 128, 9, 1, True),        # smallest problem the tcgen05 path takes, one 64-channel slab half empty
+    (2, 256, 784, 784, 9, 1, True),       # config-2 Grapher shape (7 key tiles of 112)
+    (2, 96, 300, 140, 9, 1, False),       # ragged: C not a multiple of 64, N and M not multiples of the tiles
+    (2, 64, 256, 196, 9, 2, False),       # dilation 2 -> 18-entry lists
+    (1, 128, 500, 500, 16, 2, True),      # 32-entry lists
+    (1, 256, 4096, 1024, 9, 1, False),    # 256x256 images: N = 4096 queries, r=2 pooled keys
+])
+def test_knn_tcgen05_path(dev, B, C, N, M, k, d, self_graph):
+    """The tensor-core kernel (required explicitly: GE_ERR_SHAPE if it does not apply) against the oracle
+    and against the fp32 FFMA kernels."""
+    torch.manual_seed(B * 7 + N)
+    x = torch.randn(B, C, N, 1)
+    y = None if self_graph else torch.randn(B, C, M, 1)
+    xd, yd = x.to(dev), None if y is None else y.to(dev)
+    e_tc = _knn_with_path(2, xd, yd, k, d)
+    assert _check_knn(e_tc, x, y, k, d) < 0.01
+    e_ff = _knn_with_path(1, xd, yd, k, d)
+    assert (e_tc != e_ff).float().mean() < 0.01
+
+
+def test_knn_tcgen05_tie_rule_and_scope(dev):
+    from graphecho_b200 import _cabi
+    x = torch.randn(2, 64, 256, 1, device=dev)
+    y = torch.zeros(2, 64, 256, 1, device=dev)
+    e = _knn_with_path(2, x, y, 9, 1).cpu()
+    assert torch.equal(e[0], torch.arange(9).expand(2, 256, 9))          # all keys tie -> lowest indices
+    with pytest.raises(_cabi.GraphEchoNativeError):                       # too small for the tensor-core path: loud
+        _knn_with_path(2, torch.randn(2, 256, 64, 1, device=dev), None, 9, 1)
+
+
 # ---------------------------------------------------------------------------------------- K2
 def test_mr_gather_golden(dev, golden):
     g = golden("vig")
