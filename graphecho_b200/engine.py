@@ -50,6 +50,8 @@ class EngineConfig:
     cluster_backend: str = "device"     # GModule.update_seed bipartition: 'device' | 'sklearn'
     cuda_graphs: bool = False           # capture the static segments (FPN, Grapher, discriminators) as CUDA graphs
     overlap_streams: bool = True        # GModule on a side stream, overlapped with the discriminators
+    phased_backward: bool = True        # cut autograd at the pyramid: discriminators fwd+bwd are issued before the
+                                        # host-driven GModule, so the GPU is busy while the CPU drives the graph module
     seed: int = 0
 
 
@@ -148,6 +150,29 @@ class _JointDiscriminator(nn.Module):
         return self.dis.forward_joint(feature_all, ns)
 
 
+class _Trunk(nn.Module):
+    """FPN backbone + pyramid as its own callable (its own CUDA graph): x -> (p2, p3, p4, p5)."""
+
+    def __init__(self, fpn):
+        super().__init__()
+        self.fpn = fpn
+
+    def forward(self, x):
+        return self.fpn.forward_trunk(x)
+
+
+class _Head(nn.Module):
+    """FPN smoothing + semantic head as its own callable: (p2, p3, p4, p5) -> logits.  Split from the trunk so
+    that its backward (which needs only the segmentation loss) can run while the graph module is still busy."""
+
+    def __init__(self, fpn):
+        super().__init__()
+        self.fpn = fpn
+
+    def forward(self, p2, p3, p4, p5):
+        return self.fpn.forward_head(p2, p3, p4, p5)
+
+
 class UDAEngine:
     def __init__(self, cfg: EngineConfig, device: torch.device, world_size: int = 1):
         self.cfg, self.device, self.world = cfg, device, world_size
@@ -157,6 +182,7 @@ class UDAEngine:
         self.network = self.network.to(memory_format=torch.channels_last)
         if world_size > 1 and cfg.sync_bn:
             self.network = nn.SyncBatchNorm.convert_sync_batchnorm(self.network)
+        self._trunk, self._head = _Trunk(self.network), _Head(self.network)
         self.aux: dict[str, nn.Module] = {}
         if cfg.graph_matching:
             gm = GModule(in_channels=256, num_classes=nc, device=device).to(device)
@@ -202,11 +228,17 @@ class UDAEngine:
         x = torch.zeros(n_frames, 1, cfg.hw, cfg.hw, device=dev)
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16):
             _, feats = self.network(x)
-        calls, samples, names = [self.network], [(x,)], ["network"]
+        # make_graphed_callables shares one memory pool between the graphs and relies on them being replayed in
+        # the order of this tuple (forward) and in its reverse (backward): trunk -> Grapher -> head -> discriminators
+        # forward, discriminators -> head -> Grapher -> trunk backward -- the order every step below keeps.
+        calls, samples, names = [self._trunk], [(x,)], ["trunk"]
         if cfg.graph_matching and cfg.vig_grapher:
             calls.append(self.aux["Grapher"])
             samples.append((torch.zeros_like(feats[0]).requires_grad_(),))
             names.append("Grapher")
+        calls.append(self._head)
+        samples.append(tuple(torch.zeros_like(f).requires_grad_() for f in feats))
+        names.append("head")
         if cfg.graph_matching and cfg.discriminator:
             for i, lvl in enumerate(("P2", "P3", "P4", "P5")):
                 f = feats[i]
@@ -222,8 +254,10 @@ class UDAEngine:
         # 3 warm-up executions + 1 capture of every segment's forward and backward
         self.graph_launches = (_cabi.launch_count() - before) // 4
         for name, g in zip(names, graphed):
-            if name == "network":
-                self.network = g
+            if name == "trunk":
+                self._trunk = g
+            elif name == "head":
+                self._head = g
             else:
                 self.aux[name] = g
         self.grads.zero()
@@ -249,14 +283,15 @@ class UDAEngine:
         if cfg.cuda_graphs and not self.graphed:
             self.capture_graphs(frames_src.shape[0] + frames_tgt.shape[0])
         with self._autocast():
-            logits, feats = self.network(torch.cat([frames_src, frames_tgt], dim=0))
+            feats = list(self._trunk(torch.cat([frames_src, frames_tgt], dim=0)))
+            p2g = self.aux["Grapher"](feats[0]) if cfg.graph_matching and cfg.vig_grapher else None
+            logits = self._head(*feats)
         pred_s, pred_t = logits[:ns], logits[ns:]
         losses["seg_loss"] = cfg.seg_weight * self.seg_loss(pred_s, masks_src)
         if not cfg.graph_matching:
             return losses
-        if cfg.vig_grapher:
-            with self._autocast():
-                feats = [self.aux["Grapher"](feats[0])] + list(feats[1:])
+        if p2g is not None:
+            feats = [p2g] + list(feats[1:])
         score_maps = torch.where(torch.sigmoid(pred_t) > 0.5, 1, 0)                # train_cardiac_uda.py:235
         # The graph-matching module is host-driven (two count read-backs, hundreds of tiny launches) while
         # the discriminators are four long GPU-bound graph replays with no dependency on it: run GModule on
@@ -287,14 +322,101 @@ class UDAEngine:
 
     def train_step(self, frames_src, masks_src, frames_tgt, clips_shape=None):
         self.grads.zero()
-        losses = self.forward_losses(frames_src, masks_src, frames_tgt, clips_shape)
-        total = sum(losses.values())
-        total.backward()
+        if self.cfg.phased_backward and self.cfg.graph_matching:
+            losses = self._phased_forward_backward(frames_src, masks_src, frames_tgt, clips_shape)
+            total = sum(v.detach() for v in losses.values())
+        else:
+            losses = self.forward_losses(frames_src, masks_src, frames_tgt, clips_shape)
+            total = sum(losses.values())
+            total.backward()
+            total = total.detach()
         self.grads.rebind()
         self.grads.all_reduce()
         for opt in self.opt.values():
             opt.step()
-        return total.detach(), {k: v.detach() for k, v in losses.items()}
+        return total, {k: v.detach() for k, v in losses.items()}
+
+    def _phased_forward_backward(self, frames_src, masks_src, frames_tgt, clips_shape=None):
+        """Same losses and gradients as forward_losses() + one backward(), issued in an order that keeps the GPU
+        busy.  GModule is host-driven (two count read-backs, ~900 tiny launches forward, as many backward);
+        in one autograd graph its launches sit between the pyramid and the discriminators on the CPU timeline
+        and the GPU idles for the length of them.  Here autograd is cut at the pyramid (detached leaves):
+          1. FPN trunk, FPN head (on detached pyramid leaves), Grapher forward      main stream, graph replays
+          2. discriminators forward AND backward, then the head's backward          main stream, graph replays
+          3. GModule forward and backward                                           side stream, while 2 runs
+          4. pyramid gradients = head + discriminator + GModule parts; trunk backward   main stream
+        """
+        cfg = self.cfg
+        ns = frames_src.shape[0]
+        losses = {}
+        for m in self.aux.values():
+            if isinstance(m, _JointDiscriminator):
+                if self.graphed and m.n_source not in (None, ns):
+                    raise RuntimeError("the source/target split changed after CUDA-graph capture")
+                m.n_source = ns
+        if cfg.cuda_graphs and not self.graphed:
+            self.capture_graphs(frames_src.shape[0] + frames_tgt.shape[0])
+        with self._autocast():
+            feats = list(self._trunk(torch.cat([frames_src, frames_tgt], dim=0)))
+            tops = list(feats)
+            if cfg.vig_grapher:
+                tops[0] = self.aux["Grapher"](feats[0])
+            leaves_h = [f.detach().requires_grad_() for f in feats]
+            logits = self._head(*leaves_h)
+        pred_s, pred_t = logits[:ns], logits[ns:]
+        seg = cfg.seg_weight * self.seg_loss(pred_s, masks_src)
+        losses["seg_loss"] = seg
+        score_maps = torch.where(torch.sigmoid(pred_t) > 0.5, 1, 0)                # train_cardiac_uda.py:235
+        main = torch.cuda.current_stream()
+        side = self._side_stream if cfg.overlap_streams else None
+        if side is not None:
+            side.wait_stream(main)          # the side stream waits for the pyramid only, NOT for the work issued below
+        # 2. discriminators on their own leaves, forward + backward back to back; then the head's backward
+        grads = [None] * len(tops)
+        if cfg.discriminator:
+            leaves_d = [t.detach().requires_grad_() for t in tops]
+            with self._autocast():
+                for i, lvl in enumerate(("p2", "p3", "p4", "p5")):
+                    losses[f"loss_adv_{lvl}"] = 0.1 * self.aux[f"Dis_{lvl.upper()}"](leaves_d[i])
+            for lvl in ("p5", "p4", "p3", "p2"):                                    # reverse of the forward order
+                losses[f"loss_adv_{lvl}"].backward()
+            grads = [l.grad for l in leaves_d]
+        seg.backward()                                                              # head only: stops at leaves_h
+        # 3. graph matching (and the temporal module that consumes its nodes) on the side stream
+        leaves_g = [t.detach().requires_grad_() for t in tops]
+        with torch.cuda.stream(side) if side is not None else _NullCtx():
+            _, nodes, mid = self._gmodule.forward_joint(leaves_g, ns, masks_src, score_maps)
+            losses.update(mid)
+            if cfg.temporal_graph and clips_shape is not None and nodes[0].numel() > 0 and nodes[0].dim() == 2:
+                b, t = clips_shape                                                  # train_cardiac_uda.py:300-304
+                graph_features = [f.reshape(b, t, *f.shape[1:]) for f in leaves_g]
+                tl = self.aux["TGCN"](graph_features, (nodes[0].detach(), nodes[1].detach()), self.sinkhorn, self.ce,
+                                      (None, None), r=[8, 4, 2, 1])
+                losses["temporal_graph_loss"] = sum(tl.values())
+                mid = dict(mid, temporal_graph_loss=losses["temporal_graph_loss"])
+            if mid:
+                torch.autograd.backward(list(mid.values()))
+        if side is not None:
+            main.wait_stream(side)
+        # 4. join the pyramid gradients and run the trunk (and Grapher) backward
+        out_t, out_g = [], []
+        for i, f in enumerate(feats):
+            gd, gg = grads[i], leaves_g[i].grad
+            if gg is not None and side is not None:
+                gg.record_stream(main)          # allocated on the side stream, consumed on the main stream
+            g_top = gg if gd is None else (gd if gg is None else gd + gg)          # dL/d tops[i]: discriminator + GModule
+            g_head = leaves_h[i].grad                                              # dL/d feats[i]: segmentation head
+            if tops[i] is f:
+                out_t.append(f)
+                out_g.append(g_head if g_top is None else g_head + g_top)
+            else:                                                                  # level went through the Grapher
+                out_t.append(f)
+                out_g.append(g_head)
+                if g_top is not None:
+                    out_t.append(tops[i])
+                    out_g.append(g_top)
+        torch.autograd.backward(out_t, out_g)
+        return losses
 
     @torch.no_grad()
     def predict(self, frames):

@@ -172,7 +172,9 @@ class FPN(nn.Module):
     def _upsample_add(self, x, y):
         return GF.upsample_add(x, y)
 
-    def forward(self, x):
+    def forward_trunk(self, x):
+        """Backbone + lateral / top-down pyramid (fpnseg.py:391-423): x -> [p2, p3, p4, p5] (pre-smoothing,
+        what the reference returns as `features_map`)."""
         _need_cuda(x)
         x = x.contiguous(memory_format=torch.channels_last)
         _, c2, c3, c4, c5 = self.back_bone(x)
@@ -180,7 +182,10 @@ class FPN(nn.Module):
         p4 = GF.upsample_add(p5, self.latlayer1(c4))
         p3 = GF.upsample_add(p4, self.latlayer2(c3))
         p2 = GF.upsample_add(p3, self.latlayer3(c2))
-        features_map = [p2, p3, p4, p5]
+        return p2, p3, p4, p5
+
+    def forward_head(self, p2, p3, p4, p5):
+        """Smoothing + semantic head (fpnseg.py:424-444): pyramid -> logits."""
         q4, q3, q2 = self.smooth1(p4), self.smooth2(p3), self.smooth3(p2)
         hw = q2.shape[-2:]
         g1, g2 = self.gn1, self.gn2
@@ -201,8 +206,11 @@ class FPN(nn.Module):
         s4 = narrow(wide(q4))
         s3 = narrow(q3)
         s2 = narrow(q2)
-        logits = GF.seg_tail(s2, s3, s4, s5, self.conv3.weight, self.conv3.bias, 4)
-        return logits, features_map
+        return GF.seg_tail(s2, s3, s4, s5, self.conv3.weight, self.conv3.bias, 4)
+
+    def forward(self, x):
+        p2, p3, p4, p5 = self.forward_trunk(x)
+        return self.forward_head(p2, p3, p4, p5), [p2, p3, p4, p5]
 
 
 class Discriminator(nn.Module):

@@ -351,8 +351,12 @@ class GModule(nn.Module):
                 off += count
             if len(bs) > k and self.with_cluster_update:
                 keep = self._bipartition(torch.cat([bank[cls][None, :], bs]))
-                bs = bs[keep]
-            bs = bs.mean(0)
+                # mean of the kept rows without a boolean gather (bs[keep] would synchronise the host with the
+                # clustering kernel); an empty cluster gives 0/0 = NaN exactly like the reference's mean of nothing
+                w = keep.to(bs.dtype)
+                bs = (bs * w[:, None]).sum(0) / w.sum()
+            else:
+                bs = bs.mean(0)
             mom = F.cosine_similarity(bs.unsqueeze(0), bank[cls].unsqueeze(0))
             bank[cls] = bank[cls] * mom + bs * (1.0 - mom)
 

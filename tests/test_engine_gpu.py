@@ -52,6 +52,34 @@ def test_step_losses_match_the_oracle_step(dev):
                                    msg=lambda m, k=k: f"{k}: {m}")
 
 
+def test_phased_backward_equals_single_graph_backward(dev):
+    """The step issues the discriminators' forward+backward before the host-driven GModule (autograd cut at
+    the pyramid, gradients joined by hand): losses and every parameter gradient must equal those of the plain
+    forward_losses() + one backward()."""
+    flats, totals = [], []
+    for phased in (False, True):
+        cfg = EngineConfig(hw=112, num_classes=2, bf16=False, cluster_backend="device", cuda_graphs=False,
+                           phased_backward=phased, seed=5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            eng = UDAEngine(cfg, dev)
+        _fill_engine(eng)
+        clips, masks = make_batch(cfg, n_clips=2, frames=3)
+        fs, ft, shape = split_streams(clips.to(dev))
+        torch.manual_seed(11)
+        total, losses = eng.train_step(fs, masks.to(dev), ft, shape)
+        torch.cuda.synchronize()
+        flats.append(eng.grads.flat.clone())
+        totals.append((total, losses))
+    (t0, l0), (t1, l1) = totals
+    assert set(l0) == set(l1)
+    for k in l0:
+        torch.testing.assert_close(l1[k], l0[k], rtol=1e-5, atol=1e-7, msg=lambda m, k=k: f"{k}: {m}")
+    torch.testing.assert_close(t1, t0, rtol=1e-5, atol=1e-6)
+    rel = (flats[1] - flats[0]).norm() / flats[0].norm()
+    assert rel < 1e-4, float(rel)
+    assert float(flats[0].abs().sum()) > 0
+
+
 @pytest.mark.parametrize("bf16", [False, True])
 def test_cuda_graph_step_equals_eager_step(dev, bf16):
     res = []
