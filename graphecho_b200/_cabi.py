@@ -36,6 +36,10 @@ _SIGNATURES = {
     "ge_knn_graph_set_path": (c_int, [I]),
     "ge_knn_graph_workspace_bytes": (c_size_t, [I, I, I, I]),
     "ge_knn_graph": (c_int, [P, P, P, P, P, Z, I, I, I, I, I, I, P]),
+    "ge_knn_graph_nmajor_supported": (c_int, [I, I, I, I, I, I]),
+    "ge_knn_graph_nmajor": (c_int, [P, P, I, P, P, Z, I, I, I, I, I, I, P]),
+    "ge_mrconv_gather_nmajor_fwd": (c_int, [P, P, P, P, P, I, I, I, I, I, I, P]),
+    "ge_mrconv_gather_nmajor_bwd": (c_int, [P, P, P, P, P, I, I, I, I, I, I, P]),
     "ge_mrconv_gather_fwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "ge_mrconv_gather_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "ge_tgcn_pool_concat_fwd": (c_int, [P, L, P, I, L, I, I, I, I, I, I, P]),

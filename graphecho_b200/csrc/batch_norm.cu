@@ -67,12 +67,26 @@ bn_partial_stats_kernel(const T* __restrict__ x, const float* __restrict__ shift
 // Sum the per-CTA partials of 32 channels with 8 part-lanes (CTA = 256 threads, grid = ceil(C/32)).
 __device__ __forceinline__ void reduce_parts(const float* __restrict__ part, int nparts, int C, int c, int lane8,
                                              float (*sh)[2][33], float& sa, float& sb) {
+    // 8 independent rows per trip: the loop is latency-bound (one L2 round trip per row when not unrolled,
+    // ~75 dependent trips at 592 partials), so keep 16 loads in flight per thread
     float a = 0.f, b = 0.f;
-    if (c < C)
-        for (int q = lane8; q < nparts; q += 8) {
+    if (c < C) {
+        int q = lane8;
+        for (; q + 56 < nparts; q += 64) {
+            float va[8], vb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                va[u] = part[(size_t)(q + 8 * u) * 2 * C + c];
+                vb[u] = part[(size_t)(q + 8 * u) * 2 * C + C + c];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { a += va[u]; b += vb[u]; }
+        }
+        for (; q < nparts; q += 8) {
             a += part[(size_t)q * 2 * C + c];
             b += part[(size_t)q * 2 * C + C + c];
         }
+    }
     sh[lane8][0][threadIdx.x & 31] = a;
     sh[lane8][1][threadIdx.x & 31] = b;
     __syncthreads();

@@ -542,7 +542,7 @@ extern "C" int ge_knn_graph(const float* x, const float* y, const float* relativ
                        reinterpret_cast<uintptr_t>(workspace) % 128 == 0;
     GE_REQUIRE(g_knn_path != 2 || tc_ok, GE_ERR_SHAPE,
                "ge_knn_graph: the tcgen05 path was required but does not cover B=%d C=%d N=%d M=%d K=%d", B, C, N, M, K);
-    if (tc_ok && g_knn_path != 1) return ge::knn_tc_run(x, y, edge_index, workspace, B, C, N, M, K, dilation, st);
+    if (tc_ok && g_knn_path != 1) return ge::knn_tc_run(x, y, 0, edge_index, workspace, B, C, N, M, K, dilation, st);
     float* xn = static_cast<float*>(workspace);
     float* yn = xn + (size_t)B * C * N;
     float* xsq = yn + (size_t)B * C * M;
@@ -586,4 +586,27 @@ extern "C" int ge_knn_graph(const float* x, const float* y, const float* relativ
     }
     GE_CHECK_LAUNCH("ge_knn_graph");
     return GE_OK;
+}
+
+// Node-major (channels-last) entry: x [B,N,C], y [B,M,C] or NULL, fp32 or bf16 -- the layout the FPN feature maps
+// already have, so the Grapher needs no [B,C,N] transpose.  Tensor-core path only.
+extern "C" int ge_knn_graph_nmajor_supported(int B, int C, int N, int M, int k, int dilation) {
+    return ge::knn_tc_applicable(B, C, N, M, k * dilation, false) && C % 8 == 0 ? 1 : 0;
+}
+
+extern "C" int ge_knn_graph_nmajor(const void* x, const void* y, int dtype, long long* edge_index,
+                                   void* workspace, size_t workspace_bytes,
+                                   int B, int C, int N, int M, int k, int dilation, ge_stream_t stream) {
+    GE_REQUIRE(x && edge_index && workspace, GE_ERR_ARG, "ge_knn_graph_nmajor: null pointer");
+    GE_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && k > 0 && dilation > 0, GE_ERR_ARG, "ge_knn_graph_nmajor: bad dimension");
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_knn_graph_nmajor: unsupported dtype %d", dtype);
+    const int K = k * dilation;
+    GE_REQUIRE(K <= M, GE_ERR_SHAPE, "ge_knn_graph_nmajor: k*dilation=%d exceeds the number of keys %d", K, M);
+    GE_REQUIRE(y != nullptr || N == M, GE_ERR_SHAPE, "ge_knn_graph_nmajor: self-graph needs M == N");
+    GE_REQUIRE(ge_knn_graph_nmajor_supported(B, C, N, M, k, dilation), GE_ERR_SHAPE,
+               "ge_knn_graph_nmajor: the tcgen05 path does not cover B=%d C=%d N=%d M=%d K=%d", B, C, N, M, K);
+    GE_REQUIRE(workspace_bytes >= ge::knn_tc_workspace_bytes(B, C, N, M), GE_ERR_ARG, "ge_knn_graph_nmajor: workspace too small");
+    GE_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 128 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+               (y == nullptr || reinterpret_cast<uintptr_t>(y) % 16 == 0), GE_ERR_ARG, "ge_knn_graph_nmajor: misaligned pointer");
+    return ge::knn_tc_run(x, y, dtype == GE_DTYPE_F32 ? 1 : 2, edge_index, workspace, B, C, N, M, K, dilation, (cudaStream_t)stream);
 }

@@ -152,6 +152,47 @@ knn_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* _
     }
 }
 
+// Same pre-pass for node-major input x [B,N,C] (channels-last feature maps): rows are already contiguous, so
+// one warp owns one point (8 channels per lane per trip, 128-bit bf16 / 2 x 128-bit fp32 loads), no transpose.
+template <typename T>
+__global__ void __launch_bounds__(256)
+knn_split_nmajor_kernel(const T* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                        float* __restrict__ sq, int C, int N, long long points, int sq_stride) {
+    const int lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= points) return;
+    const T* row = x + p * C;
+    float s = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        float v[8];
+        ge::load8<T>(row + c, v);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s = fmaf(v[u], v[u], s);
+    }
+    s = ge::warp_sum(s);
+    const float d = fmaxf(sqrtf(s), 1e-12f);
+    float qsum = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        float v[8];
+        ge::load8<T>(row + c, v);
+        __half2 h2[4], l2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float v0 = v[2 * u] / d, v1 = v[2 * u + 1] / d;
+            qsum = fmaf(v0, v0, qsum);
+            qsum = fmaf(v1, v1, qsum);
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            h2[u] = __halves2half2(h0, h1);
+            l2[u] = __halves2half2(__float2half_rn((v0 - __half2float(h0)) * 2048.f),
+                                   __float2half_rn((v1 - __half2float(h1)) * 2048.f));
+        }
+        *reinterpret_cast<uint4*>(hi + p * C + c) = *reinterpret_cast<const uint4*>(h2);
+        *reinterpret_cast<uint4*>(lo + p * C + c) = *reinterpret_cast<const uint4*>(l2);
+    }
+    qsum = ge::warp_sum(qsum);
+    if (lane == 0) sq[(p / N) * sq_stride + (p % N)] = qsum;
+}
+
 __global__ void knn_fill_pad_kernel(float* __restrict__ sq, int M, int Mpad, int B) {
     const int per = Mpad - M;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -498,7 +539,33 @@ size_t knn_tc_workspace_bytes(int B, int C, int N, int M) {
     return 2 * (size_t)B * C * ((size_t)N + M) * sizeof(__half) + ((size_t)B * N + (size_t)B * mpad) * sizeof(float) + 256;
 }
 
-int knn_tc_run(const float* x, const float* y, long long* edge_index, void* workspace,
+namespace {
+// layout 0: x [B,C,N] fp32 (the reference's graph layout);  1: [B,N,C] fp32;  2: [B,N,C] bf16 (node-major)
+int launch_split(const void* x, int layout, __half* hi, __half* lo, float* sq, int B, int C, int N, int sq_stride,
+                 cudaStream_t st) {
+    if (layout == 0) {
+        const size_t split_smem = (size_t)C * 33 * sizeof(float);
+        static size_t split_cached = 48 * 1024;
+        if (split_smem > split_cached) {
+            GE_CUDA(cudaFuncSetAttribute(knn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem),
+                    "ge_knn_graph(split attr)");
+            split_cached = split_smem;
+        }
+        knn_split_kernel<<<dim3(ge::cdiv(N, 32), B), 256, split_smem, st>>>(static_cast<const float*>(x), hi, lo, sq, C, N, sq_stride);
+    } else {
+        const long long points = (long long)B * N;
+        const unsigned blocks = (unsigned)ge::cdivll(points, 8);
+        if (layout == 1)
+            knn_split_nmajor_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), hi, lo, sq, C, N, points, sq_stride);
+        else
+            knn_split_nmajor_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), hi, lo, sq, C, N, points, sq_stride);
+    }
+    GE_CHECK_LAUNCH("ge_knn_graph(split)");
+    return GE_OK;
+}
+}  // namespace
+
+int knn_tc_run(const void* x, const void* y, int layout, long long* edge_index, void* workspace,
                int B, int C, int N, int M, int K, int dilation, cudaStream_t st) {
     const int BN = pick_bn(M);
     const int Mpad = ge::cdiv(M, BN) * BN;
@@ -508,22 +575,13 @@ int knn_tc_run(const float* x, const float* y, long long* edge_index, void* work
     __half* yl = yh + (y ? (size_t)B * M * C : 0);
     float* ysq = reinterpret_cast<float*>(yl + (y ? (size_t)B * M * C : 0));   // [B][Mpad], padded keys = +inf
     float* xsq = ysq + (size_t)B * Mpad;                     // [B][N]
-    const size_t split_smem = (size_t)C * 33 * sizeof(float);
-    static size_t split_cached = 48 * 1024;
-    if (split_smem > split_cached) {
-        GE_CUDA(cudaFuncSetAttribute(knn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem),
-                "ge_knn_graph(split attr)");
-        split_cached = split_smem;
-    }
+    int rc;
     if (y != nullptr) {
-        knn_split_kernel<<<dim3(ge::cdiv(N, 32), B), 256, split_smem, st>>>(x, xh, xl, xsq, C, N, N);
-        GE_CHECK_LAUNCH("ge_knn_graph(split x)");
-        knn_split_kernel<<<dim3(ge::cdiv(M, 32), B), 256, split_smem, st>>>(y, yh, yl, ysq, C, M, Mpad);
-        GE_CHECK_LAUNCH("ge_knn_graph(split y)");
+        if ((rc = launch_split(x, layout, xh, xl, xsq, B, C, N, N, st)) != GE_OK) return rc;
+        if ((rc = launch_split(y, layout, yh, yl, ysq, B, C, M, Mpad, st)) != GE_OK) return rc;
     } else {
         // self-graph: keys are the queries; the padded norm row doubles as the query norms
-        knn_split_kernel<<<dim3(ge::cdiv(N, 32), B), 256, split_smem, st>>>(x, xh, xl, ysq, C, N, Mpad);
-        GE_CHECK_LAUNCH("ge_knn_graph(split x)");
+        if ((rc = launch_split(x, layout, xh, xl, ysq, B, C, N, Mpad, st)) != GE_OK) return rc;
         yh = xh; yl = xl;
     }
     if (Mpad > M) {

@@ -107,6 +107,107 @@ mrconv_gather_bwd_scatter_kernel(const float* __restrict__ dout, const long long
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Node-major (channels-last) variant for the Grapher: x [B,N,C], y [B,M,C] (or x), out [B,N,2C] in the map's own
+// dtype (bf16 under autocast).  The centre of every edge is the point itself (what DenseDilatedKnnGraph emits).
+// One warp per point: a lane owns 8 consecutive channels, so the point's row and its k neighbour rows are read
+// as full 128-bit coalesced rows (the [B,C,N] layout reads one scattered scalar per channel and neighbour).
+template <typename T>
+__global__ void __launch_bounds__(256)
+mr_gather_nmajor_fwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const long long* __restrict__ idx0,
+                            T* __restrict__ out, unsigned char* __restrict__ argk,
+                            int C, int N, int M, int k, long long points) {
+    const int lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= points) return;
+    const long long b = p / N;
+    const int my_idx = lane < k ? (int)idx0[p * k + lane] : 0;
+    const T* ybase = y + b * (long long)M * C;
+    for (int c0 = 0; c0 < C; c0 += 256) {                    // all lanes run every trip: the shuffles need the whole warp
+        const int c = c0 + lane * 8;
+        const bool live = c < C;
+        float xi[8], best[8];
+        int arg[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { xi[u] = 0.f; best[u] = -INFINITY; arg[u] = 0; }
+        if (live) ge::load8<T>(x + p * C + c, xi);
+        for (int kk = 0; kk < k; ++kk) {
+            const int j = __shfl_sync(ge::kFull, my_idx, kk);
+            if (live) {
+                float v[8];
+                ge::load8<T>(ybase + (long long)j * C + c, v);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float d = v[u] - xi[u];
+                    if (d > best[u]) { best[u] = d; arg[u] = kk; }
+                }
+            }
+        }
+        if (!live) continue;
+        float o0[8], o1[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            o0[2 * u] = xi[u]; o0[2 * u + 1] = best[u];
+            o1[2 * u] = xi[4 + u]; o1[2 * u + 1] = best[4 + u];
+        }
+        ge::store8<T>(out + p * 2 * C + 2 * c, o0);
+        ge::store8<T>(out + p * 2 * C + 2 * c + 8, o1);
+        unsigned long long packed = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) packed |= (unsigned long long)(arg[u] & 0xff) << (8 * u);
+        *reinterpret_cast<unsigned long long*>(argk + p * C + c) = packed;
+    }
+}
+
+// dx[p][c] = dout[p][2c] - dout[p][2c+1]  (fp32 accumulator that the scatter below adds neighbour terms into)
+template <typename T>
+__global__ void __launch_bounds__(256)
+mr_gather_nmajor_bwd_init_kernel(const T* __restrict__ dout, float* __restrict__ dx, int C, long long octets) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= octets) return;
+    const int c8 = C >> 3;
+    const long long p = e / c8;
+    const int c = (int)(e - p * c8) * 8;
+    float a[8], b[8], o[8];
+    ge::load8<T>(dout + p * 2 * C + 2 * c, a);
+    ge::load8<T>(dout + p * 2 * C + 2 * c + 8, b);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { o[u] = a[2 * u] - a[2 * u + 1]; o[4 + u] = b[2 * u] - b[2 * u + 1]; }
+    ge::store8<float>(dx + p * C + c, o);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+mr_gather_nmajor_bwd_scatter_kernel(const T* __restrict__ dout, const long long* __restrict__ idx0,
+                                    const unsigned char* __restrict__ argk, float* __restrict__ dtarget,
+                                    int C, int N, int M, int k, long long points) {
+    const int lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= points) return;
+    const long long b = p / N;
+    const int my_idx = lane < k ? (int)idx0[p * k + lane] : 0;
+    float* tb = dtarget + b * (long long)M * C;
+    for (int c0 = 0; c0 < C; c0 += 256) {                    // all lanes run every trip: the shuffles need the whole warp
+        const int c = c0 + lane * 8;
+        const bool live = c < C;
+        float a[8], bq[8];
+        unsigned long long packed = 0;
+        if (live) {
+            ge::load8<T>(dout + p * 2 * C + 2 * c, a);
+            ge::load8<T>(dout + p * 2 * C + 2 * c + 8, bq);
+            packed = *reinterpret_cast<const unsigned long long*>(argk + p * C + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int kk = (int)((packed >> (8 * u)) & 0xff);
+            const int j = __shfl_sync(ge::kFull, my_idx, kk);
+            const float g = u < 4 ? a[2 * u + 1] : bq[2 * (u - 4) + 1];
+            if (live && g != 0.f) atomicAdd(tb + (long long)j * C + c + u, g);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int ge_mrconv_gather_fwd(const float* x, const float* y, const long long* idx_nbr,
@@ -145,5 +246,52 @@ extern "C" int ge_mrconv_gather_bwd(const float* dout, const long long* idx_nbr,
     mrconv_gather_bwd_scatter_kernel<<<blocks, 256, 0, st>>>(dout, idx_nbr, idx_ctr, argk, dx,
                                                              dy != nullptr ? dy : dx, C, N, M, k, total);
     GE_CHECK_LAUNCH("ge_mrconv_gather_bwd(scatter)");
+    return GE_OK;
+}
+
+// ---- node-major (channels-last) entries: x [B,N,C], y [B,M,C] or NULL, out [B,N,2C] in `dtype`; centre = the point
+extern "C" int ge_mrconv_gather_nmajor_fwd(const void* x, const void* y, const long long* idx_nbr, void* out,
+                                           unsigned char* argk, int dtype, int B, int C, int N, int M, int k,
+                                           ge_stream_t stream) {
+    GE_REQUIRE(x && idx_nbr && out && argk, GE_ERR_ARG, "ge_mrconv_gather_nmajor_fwd: null pointer");
+    GE_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && k > 0, GE_ERR_ARG, "ge_mrconv_gather_nmajor_fwd: bad dimension");
+    GE_REQUIRE(k <= 32 && C % 8 == 0, GE_ERR_SHAPE, "ge_mrconv_gather_nmajor_fwd: needs k <= 32 and C %% 8 == 0 (k=%d C=%d)", k, C);
+    GE_REQUIRE(y != nullptr || N == M, GE_ERR_SHAPE, "ge_mrconv_gather_nmajor_fwd: self-graph needs M == N");
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_mrconv_gather_nmajor_fwd: unsupported dtype %d", dtype);
+    const long long points = (long long)B * N;
+    const unsigned blocks = (unsigned)ge::cdivll(points, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GE_DTYPE_F32)
+        mr_gather_nmajor_fwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (const float*)(y ? y : x), idx_nbr,
+                                                                   (float*)out, argk, C, N, M, k, points);
+    else
+        mr_gather_nmajor_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)(y ? y : x),
+                                                                           idx_nbr, (__nv_bfloat16*)out, argk, C, N, M, k, points);
+    GE_CHECK_LAUNCH("ge_mrconv_gather_nmajor_fwd");
+    return GE_OK;
+}
+
+// dx [B,N,C] fp32 is overwritten; dy [B,M,C] fp32 must be ZERO-FILLED by the caller when y was given (NULL = self-graph).
+extern "C" int ge_mrconv_gather_nmajor_bwd(const void* dout, const long long* idx_nbr, const unsigned char* argk,
+                                           float* dx, float* dy, int dtype, int B, int C, int N, int M, int k,
+                                           ge_stream_t stream) {
+    GE_REQUIRE(dout && idx_nbr && argk && dx, GE_ERR_ARG, "ge_mrconv_gather_nmajor_bwd: null pointer");
+    GE_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && k > 0, GE_ERR_ARG, "ge_mrconv_gather_nmajor_bwd: bad dimension");
+    GE_REQUIRE(k <= 32 && C % 8 == 0, GE_ERR_SHAPE, "ge_mrconv_gather_nmajor_bwd: needs k <= 32 and C %% 8 == 0");
+    GE_REQUIRE(dy != nullptr || N == M, GE_ERR_SHAPE, "ge_mrconv_gather_nmajor_bwd: self-graph needs M == N");
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_mrconv_gather_nmajor_bwd: unsupported dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long points = (long long)B * N, octets = points * (C / 8);
+    float* target = dy != nullptr ? dy : dx;
+    if (dtype == GE_DTYPE_F32) {
+        mr_gather_nmajor_bwd_init_kernel<float><<<(unsigned)ge::cdivll(octets, 256), 256, 0, st>>>((const float*)dout, dx, C, octets);
+        GE_CHECK_LAUNCH("ge_mrconv_gather_nmajor_bwd(init)");
+        mr_gather_nmajor_bwd_scatter_kernel<float><<<(unsigned)ge::cdivll(points, 8), 256, 0, st>>>((const float*)dout, idx_nbr, argk, target, C, N, M, k, points);
+    } else {
+        mr_gather_nmajor_bwd_init_kernel<__nv_bfloat16><<<(unsigned)ge::cdivll(octets, 256), 256, 0, st>>>((const __nv_bfloat16*)dout, dx, C, octets);
+        GE_CHECK_LAUNCH("ge_mrconv_gather_nmajor_bwd(init)");
+        mr_gather_nmajor_bwd_scatter_kernel<__nv_bfloat16><<<(unsigned)ge::cdivll(points, 8), 256, 0, st>>>((const __nv_bfloat16*)dout, idx_nbr, argk, target, C, N, M, k, points);
+    }
+    GE_CHECK_LAUNCH("ge_mrconv_gather_nmajor_bwd(scatter)");
     return GE_OK;
 }

@@ -242,6 +242,75 @@ def mr_gather(x, edge_index, y=None, identity_centre=True):
     return out.unsqueeze(-1)
 
 
+# ------------------------------------------------------------------------------------------ K1/K2 node-major
+def knn_nmajor_supported(B, C, N, M, k, dilation):
+    return bool(_cabi.lib().ge_knn_graph_nmajor_supported(int(B), int(C), int(N), int(M), int(k), int(dilation)))
+
+
+@torch.no_grad()
+def knn_graph_nmajor(x, y=None, k=9, dilation=1):
+    """Node-major k-NN: x [B,N,C], y [B,M,C] or None (fp32 / bf16, dense) -> int64 edge_index [2,B,N,k]
+    (same contents as knn_graph on the [B,C,N] transposes; vig.py:369-381).  tcgen05 kernel only."""
+    _need_cuda(x, y)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    B, N, C = x.shape
+    M = N
+    if y is not None:
+        y = y.to(x.dtype).contiguous()
+        M = y.shape[1]
+    out = torch.empty((2, B, N, k), device=x.device, dtype=torch.int64)
+    nbytes = _cabi.lib().ge_knn_graph_workspace_bytes(B, C, N, M)
+    ws = torch.empty(max(nbytes, 4), device=x.device, dtype=torch.uint8)
+    call("ge_knn_graph_nmajor", ptr(x), ptr(y), _dtype_code(x), ptr(out), ptr(ws), c_size_t(ws.numel()),
+         B, C, N, M, int(k), int(dilation), stream(),
+         work=(x.element_size() * B * C * (N + M) + 16 * B * N * int(k), 2 * B * N * M * C))
+    return out
+
+
+class _MRGatherNMajor(Function):
+    @staticmethod
+    def forward(ctx, x, y, idx_nbr):
+        _need_cuda(x, y, idx_nbr)
+        x = x.contiguous()
+        B, N, C = x.shape
+        M = N
+        if y is not None:
+            y = y.to(x.dtype).contiguous()
+            M = y.shape[1]
+        i0 = idx_nbr.contiguous()
+        k = i0.shape[-1]
+        out = torch.empty((B, N, 2 * C), device=x.device, dtype=x.dtype)
+        argk = torch.empty((B, N, C), device=x.device, dtype=torch.uint8)
+        es = x.element_size()
+        call("ge_mrconv_gather_nmajor_fwd", ptr(x), ptr(y), ptr(i0), ptr(out), ptr(argk), _dtype_code(x),
+             B, C, N, M, k, stream(),
+             work=(es * B * C * (N + (M if y is not None else 0)) + 8 * B * N * k + (2 * es + 1) * B * C * N, 2 * B * C * N * k))
+        ctx.save_for_backward(i0, argk)
+        ctx.cfg = (B, C, N, M, k, y is not None, x.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        i0, argk = ctx.saved_tensors
+        B, C, N, M, k, has_y, dt = ctx.cfg
+        d = dout.to(dt).contiguous()
+        dx = torch.empty((B, N, C), device=d.device, dtype=torch.float32)
+        dy = torch.zeros((B, M, C), device=d.device, dtype=torch.float32) if has_y else None
+        es = d.element_size()
+        call("ge_mrconv_gather_nmajor_bwd", ptr(d), ptr(i0), ptr(argk), ptr(dx), ptr(dy), _dtype_code(d),
+             B, C, N, M, k, stream(), work=((2 * es + 1 + 8) * B * C * N + 8 * B * N * k, 2 * B * C * N))
+        return dx.to(dt), (dy.to(dt) if has_y else None), None
+
+
+def mr_gather_nmajor(x, idx_nbr, y=None):
+    """Node-major max-relative aggregation (vig.py:96-104 with the centre = the point itself):
+    x [B,N,C], idx_nbr [B,N,k] -> [B,N,2C] with the reference's channel interleaving."""
+    return _MRGatherNMajor.apply(x, y, idx_nbr)
+
+
 # ------------------------------------------------------------------------------------------ K6
 def _nhwc_view(t: torch.Tensor):
     """[F,C,H,W] logical tensor -> NHWC-dense tensor sharing storage when already channels_last."""

@@ -220,6 +220,18 @@ class DropPath(nn.Module):
         return x.div(keep) * mask
 
 
+def _conv_bn_train(x, conv, bn, residual=None):
+    """Training-mode BatchNorm(conv(x)) without the convolution's bias passes.  A per-channel constant in front of
+    train-mode BatchNorm cancels in the output and has zero gradient; it only shifts the batch mean, so the
+    running mean gets its `momentum * bias` share added back (state_dict parity with the reference)."""
+    y = GF.bn_act(F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups), bn,
+                  residual=residual, relu=False)
+    if conv.bias is not None and bn.track_running_stats:
+        with torch.no_grad():
+            bn.running_mean.add_(conv.bias.detach().to(bn.running_mean.dtype), alpha=float(bn.momentum))
+    return y
+
+
 class Grapher(nn.Module):
     """fc1 (1x1 conv + BN) -> DyGraphConv2d -> fc2 (1x1 conv + BN) -> + residual (vig.py:384-430)."""
 
@@ -244,10 +256,48 @@ class Grapher(nn.Module):
         N = H * W
         return F.interpolate(relative_pos.unsqueeze(0), size=(N, N // (self.r * self.r)), mode="bicubic").squeeze(0)
 
+    def _node_major_ok(self, x):
+        """The channels-last fast path: max-relative conv, BatchNorm, no relative position bias, and a problem the
+        tcgen05 k-NN kernel covers.  Everything else takes the reference-shaped [B,C,N,1] route below."""
+        gc = self.graph_conv
+        B, C, H, W = x.shape
+        N = H * W
+        M = (H // self.r) * (W // self.r) if self.r > 1 else N
+        seq = getattr(gc.gconv, "nn", None)
+        return (x.is_cuda and self.relative_pos is None and isinstance(gc.gconv, MRConv2d) and seq is not None
+                and len(seq) == 3 and type(seq[1]) is nn.BatchNorm2d and isinstance(self.drop_path, nn.Identity)
+                and not gc.dilated_knn_graph._dilated.stochastic and gc.k <= 32
+                and GF.knn_nmajor_supported(B, C, N, M, gc.k, gc.d))
+
+    def _forward_node_major(self, x, shortcut):
+        """Grapher body on the NHWC map itself: its [B, H*W, C] view IS the node-major graph tensor, so the k-NN
+        build, the max-relative gather (bf16 in, bf16 out under autocast), the grouped 1x1 conv and both
+        BatchNorms run without a single layout change or fp32 copy (the [B,C,N,1] route makes four)."""
+        gc = self.graph_conv
+        B, C, H, W = x.shape
+        xn = x.permute(0, 2, 3, 1).reshape(B, H * W, C)                  # view of the channels_last storage
+        yn = None
+        if self.r > 1:
+            y = F.avg_pool2d(x, self.r, self.r).contiguous(memory_format=torch.channels_last)
+            yn = y.permute(0, 2, 3, 1).reshape(B, -1, C)
+        edge = GF.knn_graph_nmajor(xn, yn, gc.k, gc.d)[0]
+        feat = GF.mr_gather_nmajor(xn, edge, yn)                         # [B,N,2C], reference channel interleaving
+        f4 = feat.view(B, H, W, 2 * C).permute(0, 3, 1, 2)               # logical NCHW, channels_last strides
+        conv, bn, act = gc.gconv.nn[0], gc.gconv.nn[1], gc.gconv.nn[2]
+        y = act(_conv_bn_train(f4, conv, bn))
+        return _conv_bn_train(y, self.fc2[0], self.fc2[1], residual=shortcut)
+
     def forward(self, x):
         shortcut = x
-        x = GF.bn_act(self.fc1[0](x), self.fc1[1], relu=False)
+        fast = x.is_cuda and self.training and all(type(m) is nn.BatchNorm2d and m.momentum is not None
+                                                   for m in (self.fc1[1], self.fc2[1]))
+        if fast:
+            x = _conv_bn_train(x, self.fc1[0], self.fc1[1])
+        else:
+            x = GF.bn_act(self.fc1[0](x), self.fc1[1], relu=False)
         _, _, H, W = x.shape
+        if fast and self._node_major_ok(x):
+            return self._forward_node_major(x.contiguous(memory_format=torch.channels_last), shortcut)
         x = self.graph_conv(x, self._get_relative_pos(self.relative_pos, H, W))
         if isinstance(self.drop_path, nn.Identity):
             return GF.bn_act(self.fc2[0](x), self.fc2[1], residual=shortcut, relu=False)   # BN + residual in one pass

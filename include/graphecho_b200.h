@@ -103,6 +103,14 @@ int ge_knn_graph(const float* x, const float* y, const float* relative_pos, long
                  void* workspace, size_t workspace_bytes,
                  int B, int C, int N, int M, int k, int dilation, ge_stream_t stream);
 
+/* Node-major (channels-last) entry for the Grapher: x [B,N,C], y [B,M,C] or NULL in `dtype` (fp32 / bf16) -- the
+ * layout the FPN feature maps already have.  tcgen05 path only: ge_knn_graph_nmajor_supported() says whether
+ * it covers the problem (else transpose and call ge_knn_graph).  Same workspace size as ge_knn_graph. */
+int ge_knn_graph_nmajor_supported(int B, int C, int N, int M, int k, int dilation);
+int ge_knn_graph_nmajor(const void* x, const void* y, int dtype, long long* edge_index,
+                        void* workspace, size_t workspace_bytes,
+                        int B, int C, int N, int M, int k, int dilation, ge_stream_t stream);
+
 /* ---- K2: max-relative aggregation (gather half of MRConv2d) -------------------------------
  * models/vig.py:96-104 + batched_index_select (:209-229):
  * out[b,2c,n] = x[b,c,n]; out[b,2c+1,n] = max_k(y[b,c,idx_nbr[b,n,k]] - x[b,c,idx_ctr[b,n,k]]).
@@ -115,6 +123,15 @@ int ge_mrconv_gather_fwd(const float* x, const float* y, const long long* idx_nb
 int ge_mrconv_gather_bwd(const float* dout, const long long* idx_nbr, const long long* idx_ctr,
                          const unsigned char* argk, float* dx, float* dy,
                          int B, int C, int N, int M, int k, ge_stream_t stream);
+/* Node-major variants (centre of every edge = the point itself): x [B,N,C], y [B,M,C] or NULL, out [B,N,2C] in
+ * `dtype` with out[..,2c] = x[..,c], out[..,2c+1] = max_k(y[nbr_k,c] - x[n,c]); argk uint8 [B,N,C].
+ * Backward: dx [B,N,C] fp32 overwritten, dy [B,M,C] fp32 zero-filled by the caller (NULL for a self-graph). */
+int ge_mrconv_gather_nmajor_fwd(const void* x, const void* y, const long long* idx_nbr, void* out,
+                                unsigned char* argk, int dtype, int B, int C, int N, int M, int k,
+                                ge_stream_t stream);
+int ge_mrconv_gather_nmajor_bwd(const void* dout, const long long* idx_nbr, const unsigned char* argk,
+                                float* dx, float* dy, int dtype, int B, int C, int N, int M, int k,
+                                ge_stream_t stream);
 
 /* ---- K6: TGCN pyramid pooling + concat ------------------------------------------------------
  * avg_pool2d(r) per level + channel concat of TGCN.DyGraphConv2d.forward (models/TGCN.py:62-70),

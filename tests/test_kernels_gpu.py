@@ -235,6 +235,51 @@ def test_knn_tcgen05_tie_rule_and_scope(dev):
         _knn_with_path(2, torch.randn(2, 256, 64, 1, device=dev), None, 9, 1)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("self_graph", [True, False])
+def test_knn_node_major_equals_channel_major(dev, dtype, self_graph):
+    """ge_knn_graph_nmajor on x [B,N,C] == ge_knn_graph on the [B,C,N] transpose of the same values."""
+    torch.manual_seed(3)
+    B, C, N, M, k = 3, 96, 400, 400 if self_graph else 196, 9
+    x = torch.randn(B, N, C, device=dev).to(dtype)
+    y = None if self_graph else torch.randn(B, M, C, device=dev).to(dtype)
+    assert GF.knn_nmajor_supported(B, C, N, M, k, 1)
+    e_nm = GF.knn_graph_nmajor(x, y, k, 1)
+    xt = x.float().transpose(1, 2).contiguous().unsqueeze(-1)
+    yt = None if y is None else y.float().transpose(1, 2).contiguous().unsqueeze(-1)
+    e_cm = GF.knn_graph(xt, yt, k, 1)
+    assert (e_nm != e_cm).float().mean() < 0.002
+    assert _check_knn(e_nm, xt.cpu(), None if yt is None else yt.cpu(), k, 1) < 0.01
+    assert not GF.knn_nmajor_supported(B, C, 64, 64, k, 1)          # small graphs stay on the [B,C,N] route
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("self_graph", [True, False])
+def test_mr_gather_node_major_vs_oracle(dev, dtype, self_graph):
+    torch.manual_seed(7)
+    B, C, N, M, k = 2, 40, 150, 150 if self_graph else 61, 9
+    x = torch.randn(B, N, C).to(dtype)
+    y = None if self_graph else torch.randn(B, M, C).to(dtype)
+    e0 = torch.randint(0, M, (B, N, k))
+    edge = torch.stack([e0, torch.arange(N).view(1, N, 1).expand(B, N, k)])
+    xo = x.float().transpose(1, 2).unsqueeze(-1).clone().requires_grad_()
+    yo = None if y is None else y.float().transpose(1, 2).unsqueeze(-1).clone().requires_grad_()
+    ref = V.max_relative(xo, edge, yo)                                   # [B,2C,N,1]
+    W = torch.randn(B, N, 2 * C).to(dtype)
+    (ref.squeeze(-1).transpose(1, 2) * W.float()).sum().backward()
+    xd = x.to(dev).requires_grad_()
+    yd = None if y is None else y.to(dev).requires_grad_()
+    out = GF.mr_gather_nmajor(xd, e0.to(dev), yd)
+    assert out.dtype == dtype and out.shape == (B, N, 2 * C)
+    tol = dict(rtol=0, atol=0) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    close(out.float(), ref.squeeze(-1).transpose(1, 2), **tol)
+    (out.float() * W.to(dev).float()).sum().backward()
+    gtol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    close(xd.grad.float(), xo.grad.squeeze(-1).transpose(1, 2), **gtol)
+    if y is not None:
+        close(yd.grad.float(), yo.grad.squeeze(-1).transpose(1, 2), **gtol)
+
+
 # ---------------------------------------------------------------------------------------- K2
 def test_mr_gather_golden(dev, golden):
     g = golden("vig")

@@ -104,6 +104,30 @@ def test_grapher_and_mrconv(dev, golden):
         close(gr.fc1[1].running_var, c["rv"], rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("r", [1, 2])
+def test_grapher_node_major_path_equals_reference_layout_path(dev, r):
+    """At N >= 128 the Grapher runs on the channels-last map itself (node-major k-NN + gather, no [B,C,N,1]
+    copies).  Same module, same input: output, input gradient, parameter gradients and BatchNorm statistics must
+    equal the reference-shaped route (which the golden fixtures pin at N = 64)."""
+    torch.manual_seed(0)
+    C, H = 32, 16 * r
+    res = []
+    for fast in (True, False):
+        gr = fill_module(vig.Grapher(C, 9, 1, "mr", "gelu", "batch", True, False, 0.0, r, H * H, 0.0, False),
+                         prefix=f"grapher_r{r}.").to(dev).train()
+        if not fast:
+            gr._node_major_ok = lambda x: False
+        torch.manual_seed(1)
+        xin = torch.randn(3, C, H, H, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_()
+        out = gr(xin)
+        out.square().mean().backward()
+        res.append((out.detach(), xin.grad, gr.fc2[0].weight.grad, gr.graph_conv.gconv.nn[0].weight.grad,
+                    gr.graph_conv.gconv.nn[1].running_var.clone(), gr.fc2[1].running_mean.clone()))
+    assert vig.Grapher._node_major_ok(gr, torch.empty(3, C, H, H, device=dev))      # the fast path really applies
+    for a, b in zip(*res):
+        close(a, b, rtol=2e-3, atol=1e-5)
+
+
 @pytest.mark.parametrize("bb,nc,hw", [("resnet", 1, 112), ("VGG16", 3, 64)])
 def test_fpn_matches_reference(dev, golden, bb, nc, hw):
     g = golden("fpn")
