@@ -206,7 +206,9 @@ class UDAEngine:
             m.train()
         self.grads = FlatGradSync(modules)
         self.graphed = False
-        self._side_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        # high priority: the graph module's hundreds of tiny kernels (and the two read-backs its host code waits on)
+        # must not queue behind the waves of the discriminator / head kernels they overlap with
+        self._side_stream = torch.cuda.Stream(device=device, priority=-1) if device.type == "cuda" else None
         self.graph_launches = 0      # graphecho_b200 kernels replayed per step inside the CUDA graphs
         self.opt = {"Net": torch.optim.Adam(self.network.parameters(), lr=cfg.lr_net, betas=(0.9, 0.999),
                                             weight_decay=cfg.weight_decay, fused=device.type == "cuda")}

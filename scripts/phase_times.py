@@ -35,9 +35,11 @@ def timed_bw(*a, **k):
     t0 = time.perf_counter()
     r = orig_bw(*a, **k)
     marks.setdefault("bw_cpu_ms", []).append((time.perf_counter() - t0) * 1e3)
+    ev = torch.cuda.Event(enable_timing=True); ev.record(torch.cuda.current_stream())
+    marks.setdefault("bw_ev", []).append(ev)
     return r
 torch.autograd.backward = timed_bw
-for it in range(3):
+for it in range(8):
     marks.clear()
     torch.cuda.synchronize()
     ev_a = torch.cuda.Event(enable_timing=True); ev_b = torch.cuda.Event(enable_timing=True)
@@ -46,5 +48,7 @@ for it in range(3):
     t_cpu = (time.perf_counter() - t0) * 1e3
     ev_b.record(); torch.cuda.synchronize()
     e0, e1 = marks["ev"]
+    bev = marks["bw_ev"]
+    print("backward() calls end at (ms into step, on their stream):", [round(ev_a.elapsed_time(e), 2) for e in bev])
     print(f"step gpu {ev_a.elapsed_time(ev_b):.2f} ms, cpu issue {t_cpu:.2f} ms | GModule fwd: cpu {marks['gm_fwd_cpu_ms']:.2f} ms, side-stream {e0.elapsed_time(e1):.2f} ms"
           f" (starts {ev_a.elapsed_time(e0):.2f} ms into the step) | backward() cpu ms: {[round(x,2) for x in marks['bw_cpu_ms']]}")
