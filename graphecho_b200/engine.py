@@ -187,6 +187,7 @@ class UDAEngine:
         if cfg.graph_matching:
             gm = GModule(in_channels=256, num_classes=nc, device=device).to(device)
             gm.cluster_backend = cfg.cluster_backend
+            gm.defer_seed_update = cfg.phased_backward      # the phased step flushes it after the last launch
             self.aux["Graph"] = gm
             self._gmodule = gm
         if cfg.discriminator and cfg.graph_matching:
@@ -358,6 +359,10 @@ class UDAEngine:
                 m.n_source = ns
         if cfg.cuda_graphs and not self.graphed:
             self.capture_graphs(frames_src.shape[0] + frames_tgt.shape[0])
+        main = torch.cuda.current_stream()
+        side = self._side_stream if cfg.overlap_streams else None
+        if side is not None:
+            side.wait_stream(main)          # inputs (e.g. the step's host->device copies) are ready for the side stream
         with self._autocast():
             feats = list(self._trunk(torch.cat([frames_src, frames_tgt], dim=0)))
             tops = list(feats)
@@ -365,12 +370,14 @@ class UDAEngine:
                 tops[0] = self.aux["Grapher"](feats[0])
             leaves_h = [f.detach().requires_grad_() for f in feats]
             logits = self._head(*leaves_h)
+        # while the GPU runs the forward graphs: the source half of the sampler plan (needs the masks and the map
+        # sizes only) and its count read-back, on the otherwise idle side stream
+        with torch.cuda.stream(side) if side is not None else _NullCtx():
+            self._gmodule.prepare_source(masks_src, [f.shape[-2:] for f in feats], masks_src.device)
         pred_s, pred_t = logits[:ns], logits[ns:]
         seg = cfg.seg_weight * self.seg_loss(pred_s, masks_src)
         losses["seg_loss"] = seg
         score_maps = torch.where(torch.sigmoid(pred_t) > 0.5, 1, 0)                # train_cardiac_uda.py:235
-        main = torch.cuda.current_stream()
-        side = self._side_stream if cfg.overlap_streams else None
         if side is not None:
             side.wait_stream(main)          # the side stream waits for the pyramid only, NOT for the work issued below
         # 2. discriminators on their own leaves, forward + backward back to back; then the head's backward
@@ -418,6 +425,11 @@ class UDAEngine:
                     out_t.append(tops[i])
                     out_g.append(g_top)
         torch.autograd.backward(out_t, out_g)
+        # everything is issued: the seed-bank update (next step's input) runs while the GPU finishes the backward
+        with torch.cuda.stream(side) if side is not None else _NullCtx():
+            self._gmodule.flush_seed_update()
+        if side is not None:
+            main.wait_stream(side)
         return losses
 
     @torch.no_grad()

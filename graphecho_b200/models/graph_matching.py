@@ -146,17 +146,41 @@ class GModule(nn.Module):
         with torch.autocast("cuda", enabled=False):
             return self._train_fp32(None, (features_all, 0), (features_all, int(n_source)), targets, score_maps)
 
+    def prepare_source(self, targets, feature_shapes, device):
+        """The source half of the sampler plan depends on the ground-truth masks and the map SIZES only, not on the
+        network: a caller that knows the sizes can issue it (and its count read-back) while the network forward is
+        still running.  The next training forward consumes the result (train_cardiac_uda.py:247-256 calls the
+        graph module with the same masks)."""
+        shapes = [torch.empty((0, 0, int(h), int(w)), device=device) for h, w in feature_shapes]
+        plan = self.graph_generator.plan(self.compute_locations(shapes), self.find_bbox(targets))
+        self._prepared_source = (targets, plan[0], plan[1].tolist())
+
+    def flush_seed_update(self):
+        """Run a seed-bank update that `defer_seed_update=True` postponed (the banks are only read by the next
+        step's hallucination, so the update -- host-driven: clustering launches, ~200 small ops -- can wait
+        until the rest of the step has been issued)."""
+        pending, self._pending_seed = getattr(self, "_pending_seed", None), None
+        if pending is not None:
+            self._class_layout = pending[4]
+            self.update_seed(*pending[:4])
+
     def _train_fp32(self, features, src, tgt, targets, score_maps):
         losses = {}
+        self.flush_seed_update()
         self._sync_seed_stream()
         (feat_s, off_s), (feat_t, off_t) = src, tgt
-        boxes_s, boxes_t = self.find_bbox(targets), self.find_bbox(score_maps)
         gen = self.graph_generator
-        plan_s = gen.plan(self.compute_locations(feat_s), boxes_s)
-        plan_t = gen.plan(self.compute_locations(feat_t), boxes_t)
-        counts = torch.stack([plan_s[1], plan_t[1]]).tolist()                      # ONE host sync for both domains
-        nodes_1, labels_1, weights_1 = gen.gather(feat_s, plan_s[0], counts[0], off_s)
-        nodes_2, labels_2, weights_2 = gen.gather(feat_t, plan_t[0], counts[1], off_t)
+        prepared, self._prepared_source = getattr(self, "_prepared_source", None), None
+        plan_t = gen.plan(self.compute_locations(feat_t), self.find_bbox(score_maps))
+        if prepared is not None and prepared[0] is targets:
+            labels_s, counts_s = prepared[1], prepared[2]
+            counts_t = plan_t[1].tolist()                                           # host sync: target counts only
+        else:
+            plan_s = gen.plan(self.compute_locations(feat_s), self.find_bbox(targets))
+            labels_s = plan_s[0]
+            counts_s, counts_t = torch.stack([plan_s[1], plan_t[1]]).tolist()       # ONE host sync for both domains
+        nodes_1, labels_1, weights_1 = gen.gather(feat_s, labels_s, counts_s, off_s)
+        nodes_2, labels_2, weights_2 = gen.gather(feat_t, plan_t[0], counts_t, off_t)
         if nodes_1.size(0) < 6 or nodes_1.dim() == 1:                             # graph_matching.py:259-260
             return features, (nodes_1, nodes_2), losses
         nodes_1, nodes_2 = nodes_1.float(), nodes_2.float()
@@ -168,7 +192,11 @@ class GModule(nn.Module):
         if self.with_complete_graph:
             nodes_1, edges_1 = self._forward_intra_domain_graph(nodes_1)
             nodes_2, edges_2 = self._forward_intra_domain_graph(nodes_2)
-        self.update_seed(nodes_1, labels_1, nodes_2, labels_2)
+        if getattr(self, "defer_seed_update", False):
+            self._pending_seed = (nodes_1.detach(), labels_1, nodes_2.detach(), labels_2, getattr(self, "_class_layout", None))
+            self._class_layout = None
+        else:
+            self.update_seed(nodes_1, labels_1, nodes_2, labels_2)
         if self.with_node_dis and self.node_dis_place == "intra":
             losses["dis_loss"] = self._node_dis_loss(nodes_1, nodes_2)
         if self.with_domain_interaction:
@@ -373,8 +401,15 @@ class GModule(nn.Module):
 
     # ------------------------------------------------------------------ locations and boxes
     def compute_locations(self, features):
-        return [self.compute_locations_per_level(f.size(-2), f.size(-1), self.fpn_strides[l], f.device)
-                for l, f in enumerate(features)]
+        """Per-level location grids (graph_matching.py:609-635).  They depend on the map sizes only, so they are
+        built once per shape set and reused (the reference rebuilds ~30 small tensors per domain per step)."""
+        key = tuple((f.size(-2), f.size(-1), str(f.device)) for f in features)
+        cache = getattr(self, "_loc_cache", None)
+        if cache is None or cache[0] != key:
+            locs = [self.compute_locations_per_level(f.size(-2), f.size(-1), self.fpn_strides[l], f.device)
+                    for l, f in enumerate(features)]
+            self._loc_cache = cache = (key, locs)
+        return cache[1]
 
     def compute_locations_per_level(self, h, w, stride, device):
         ys = torch.arange(0, h * stride, step=stride, dtype=torch.float32, device=device)
