@@ -35,6 +35,40 @@ def _free_port():
     return p
 
 
+def _worker_unbound(rank, world, port, out):
+    """bind=False: gradients stay autograd's own tensors and are packed into the flat buffer for the exchange."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    unused = torch.nn.Linear(3, 3)
+    sync = FlatGradSync([net, unused], bind=False)
+    full = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+    tgt = torch.randn(8, 2, generator=torch.Generator().manual_seed(2))
+    idx = list(shard_range(8, rank, world))
+    ok = True
+    for _ in range(2):                                  # second round: .grad is a flat view when zero() runs
+        sync.zero()
+        ok = ok and all(p.grad is None for p in net.parameters())
+        ((net(full[idx]) - tgt[idx]) ** 2).mean().backward()
+        sync.all_reduce()
+        ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        ref.load_state_dict(net.state_dict())
+        ((ref(full) - tgt) ** 2).mean().backward()
+        ok = ok and all(torch.allclose(p.grad, q.grad, atol=1e-6) for p, q in zip(net.parameters(), ref.parameters()))
+        ok = ok and float(unused.weight.grad.abs().sum()) == 0.0
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_unbound_grad_exchange_matches_single_process():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_unbound, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -68,7 +68,7 @@ def test_phased_backward_equals_single_graph_backward(dev):
         torch.manual_seed(11)
         total, losses = eng.train_step(fs, masks.to(dev), ft, shape)
         torch.cuda.synchronize()
-        flats.append(eng.grads.flat.clone())
+        flats.append(eng.grads.pack().clone())
         totals.append((total, losses))
     (t0, l0), (t1, l1) = totals
     assert set(l0) == set(l1)
