@@ -300,6 +300,129 @@ gn_relu_up_bwd_apply_kernel(const T* __restrict__ dout, const float* __restrict_
     }
 }
 
+
+// Same-size variant of phase 1: no bilinear adjoint in the loop, four channels per thread, four pixels of both
+// streams in flight; 64 registers so that two 512-thread CTAs share an SM and all samples of a 256-frame batch
+// run in one wave (the general kernel: 91 registers, one CTA per SM, two uneven waves).
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS, 2)
+gn_relu_bwd_reduce_same_kernel(const T* __restrict__ dout, const T* __restrict__ x,
+                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               float* __restrict__ S1, float* __restrict__ S2,
+                               float* __restrict__ A1, float* __restrict__ A2, int hw, int C, int cpg) {
+    extern __shared__ __align__(16) float sm[];
+    const int c4 = C >> 2, nPL = GN_THREADS / c4;
+    float* s1 = sm;
+    float* s2 = sm + (size_t)nPL * C;
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int co = tid % c4, pl = tid / c4, cc = co * 4;
+    float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pl < nPL) {
+        const size_t so = (size_t)n * C + cc;
+        const float4 m4 = *reinterpret_cast<const float4*>(mean + so), r4 = *reinterpret_cast<const float4*>(rstd + so);
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + cc), b4 = *reinterpret_cast<const float4*>(beta + cc);
+        const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+        float sc[4], sh[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sc[u] = r[u] * g[u]; sh[u] = b[u] - m[u] * sc[u]; }
+        const T* xb = x + (size_t)n * hw * C + cc;
+        const T* db = dout + (size_t)n * hw * C + cc;
+        for (int p0 = pl; p0 < hw; p0 += 4 * nPL) {
+            Vec4<T> xv[4], dv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int p = p0 + q * nPL;
+                if (p < hw) { xv[q].load(xb + (size_t)p * C); dv[q].load(db + (size_t)p * C); }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (p0 + q * nPL >= hw) break;
+                float xf[4], df[4];
+                xv[q].get(xf); dv[q].get(df);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float d = (fmaf(xf[u], sc[u], sh[u]) > 0.f) ? df[u] : 0.f;
+                    a1[u] += d;
+                    a2[u] = fmaf(d, (xf[u] - m[u]) * r[u], a2[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { s1[pl * C + cc + u] = a1[u]; s2[pl * C + cc + u] = a2[u]; }
+    }
+    __syncthreads();
+    const float inv = 1.f / ((float)hw * (float)cpg);
+    for (int c = tid; c < C; c += GN_THREADS) {
+        float sa = 0.f, sb = 0.f;
+        for (int q = 0; q < nPL; ++q) { sa += s1[q * C + c]; sb += s2[q * C + c]; }
+        S1[(size_t)n * C + c] = sa;
+        S2[(size_t)n * C + c] = sb;
+        const float gm = gamma[c];
+        float ga = gm * sa, gb = gm * sb;
+        if (cpg > 1) { ga = group_lane_sum(ga, cpg); gb = group_lane_sum(gb, cpg); }
+        A1[(size_t)n * C + c] = ga * inv;
+        A2[(size_t)n * C + c] = gb * inv;
+    }
+}
+
+// Same-size variant of phase 2 (the discriminator towers and the same-size head branches: 19 of the 23 calls of a
+// config-2 step).  A thread owns FOUR channels (one 64-bit bf16 access) of GPIX consecutive pixels: half the
+// per-thread state of the octet kernel above (134 registers, 11 % occupancy, 20 % of HBM peak in the round-1
+// ncu capture), so three times as many warps are in flight.  dx = c0*dyh - c1 - (x-m)*c2 with the per-(n,c)
+// constants folded once.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_relu_bwd_apply_same_kernel(const T* __restrict__ dout, const T* __restrict__ x,
+                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              const float* __restrict__ A1, const float* __restrict__ A2, T* __restrict__ dx,
+                              int hw, int C, long long total) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int c4 = C >> 2;
+    const int cc = (int)(e % c4) * 4;
+    const int groups = (hw + GPIX - 1) / GPIX;
+    const long long pg = e / c4;
+    const int n = (int)(pg / groups);
+    const int q0 = (int)(pg - (long long)n * groups) * GPIX;
+    const size_t sc_off = (size_t)n * C + cc;
+    const float4 m4 = *reinterpret_cast<const float4*>(mean + sc_off), r4 = *reinterpret_cast<const float4*>(rstd + sc_off);
+    const float4 g4 = *reinterpret_cast<const float4*>(gamma + cc), b4 = *reinterpret_cast<const float4*>(beta + cc);
+    const float4 p4 = *reinterpret_cast<const float4*>(A1 + sc_off), s4 = *reinterpret_cast<const float4*>(A2 + sc_off);
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float a1[4] = {p4.x, p4.y, p4.z, p4.w}, a2[4] = {s4.x, s4.y, s4.z, s4.w};
+    float c0[4], c1[4], c2[4], sh[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        c0[u] = r[u] * g[u];                 // also the folded scale of the forward affine
+        c1[u] = r[u] * a1[u];
+        c2[u] = r[u] * r[u] * a2[u];
+        sh[u] = b[u] - m[u] * c0[u];
+    }
+    const size_t base = (size_t)n * hw * C + cc;
+    Vec4<T> xv[GPIX], dv[GPIX];
+#pragma unroll
+    for (int q = 0; q < GPIX; ++q)
+        if (q0 + q < hw) { xv[q].load(x + base + (size_t)(q0 + q) * C); dv[q].load(dout + base + (size_t)(q0 + q) * C); }
+#pragma unroll
+    for (int q = 0; q < GPIX; ++q) {
+        if (q0 + q >= hw) break;
+        float xf[4], df[4], res[4];
+        xv[q].get(xf); dv[q].get(df);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float d = (fmaf(xf[u], c0[u], sh[u]) > 0.f) ? df[u] : 0.f;
+            res[u] = c0[u] * d - c1[u] - (xf[u] - m[u]) * c2[u];
+        }
+        Vec4<T> o;
+        o.set(res);
+        o.store(dx + base + (size_t)(q0 + q) * C);
+    }
+}
+
 bool gn_shape_ok(int C, int cpg) {
     if (C % 8 != 0 || C / 8 > GN_THREADS || GN_THREADS % (C / 8) != 0) return false;
     if (cpg < 1 || C % cpg != 0) return false;
@@ -379,23 +502,44 @@ extern "C" int ge_gn_relu_upsample_bwd(const void* dout, const void* x, const fl
     const size_t smem = gn_smem(C);
     const long long total8 = (long long)N * ge::cdiv(h * w, GPIX) * (C / 8);
     const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
+    const long long total4 = total8 * 2;
+    // the same-size reduce kernel: 4 channels per thread, [nPL][C] x 2 floats of shared memory (<= 48 KB by construction)
+    const bool same_ok = C / 4 <= GN_THREADS && GN_THREADS % (C / 4) == 0;
+    const size_t smem_same = same_ok ? (size_t)2 * (GN_THREADS / (C / 4)) * C * sizeof(float) : 0;
+    const unsigned blocks4 = (unsigned)ge::cdivll(total4, 256);
     static size_t c0 = 0, c1 = 0;
     if (dtype == GE_DTYPE_F32) {
         int rc = set_smem_once(gn_relu_up_bwd_reduce_kernel<float>, smem, c0, "ge_gn_relu_upsample_bwd(attr)");
         if (rc) return rc;
-        gn_relu_up_bwd_reduce_kernel<float><<<N, GN_THREADS, smem, st>>>((const float*)dout, (const float*)x, mean, rstd,
-            gamma, beta, dyh, S1, S2, A1, A2, h, w, H, W, C, channels_per_group);
+        if (ident && same_ok)
+            gn_relu_bwd_reduce_same_kernel<float><<<N, GN_THREADS, smem_same, st>>>((const float*)dout, (const float*)x, mean, rstd,
+                gamma, beta, S1, S2, A1, A2, h * w, C, channels_per_group);
+        else
+            gn_relu_up_bwd_reduce_kernel<float><<<N, GN_THREADS, smem, st>>>((const float*)dout, (const float*)x, mean, rstd,
+                gamma, beta, dyh, S1, S2, A1, A2, h, w, H, W, C, channels_per_group);
         GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(reduce)");
-        gn_relu_up_bwd_apply_kernel<float><<<blocks, 256, 0, st>>>((const float*)dout, dyh, (const float*)x, mean, rstd,
-            gamma, beta, A1, A2, (float*)dx, h * w, C, ident, total8);
+        if (ident)
+            gn_relu_bwd_apply_same_kernel<float><<<blocks4, 256, 0, st>>>((const float*)dout, (const float*)x, mean, rstd,
+                gamma, beta, A1, A2, (float*)dx, h * w, C, total4);
+        else
+            gn_relu_up_bwd_apply_kernel<float><<<blocks, 256, 0, st>>>((const float*)dout, dyh, (const float*)x, mean, rstd,
+                gamma, beta, A1, A2, (float*)dx, h * w, C, ident, total8);
     } else if (dtype == GE_DTYPE_BF16) {
         int rc = set_smem_once(gn_relu_up_bwd_reduce_kernel<bf16>, smem, c1, "ge_gn_relu_upsample_bwd(attr)");
         if (rc) return rc;
-        gn_relu_up_bwd_reduce_kernel<bf16><<<N, GN_THREADS, smem, st>>>((const bf16*)dout, (const bf16*)x, mean, rstd,
-            gamma, beta, dyh, S1, S2, A1, A2, h, w, H, W, C, channels_per_group);
+        if (ident && same_ok)
+            gn_relu_bwd_reduce_same_kernel<bf16><<<N, GN_THREADS, smem_same, st>>>((const bf16*)dout, (const bf16*)x, mean, rstd,
+                gamma, beta, S1, S2, A1, A2, h * w, C, channels_per_group);
+        else
+            gn_relu_up_bwd_reduce_kernel<bf16><<<N, GN_THREADS, smem, st>>>((const bf16*)dout, (const bf16*)x, mean, rstd,
+                gamma, beta, dyh, S1, S2, A1, A2, h, w, H, W, C, channels_per_group);
         GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(reduce)");
-        gn_relu_up_bwd_apply_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)dout, dyh, (const bf16*)x, mean, rstd,
-            gamma, beta, A1, A2, (bf16*)dx, h * w, C, ident, total8);
+        if (ident)
+            gn_relu_bwd_apply_same_kernel<bf16><<<blocks4, 256, 0, st>>>((const bf16*)dout, (const bf16*)x, mean, rstd,
+                gamma, beta, A1, A2, (bf16*)dx, h * w, C, total4);
+        else
+            gn_relu_up_bwd_apply_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)dout, dyh, (const bf16*)x, mean, rstd,
+                gamma, beta, A1, A2, (bf16*)dx, h * w, C, ident, total8);
     } else { ge_set_error("ge_gn_relu_upsample_bwd: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_gn_relu_upsample_bwd(apply)");
     return GE_OK;
