@@ -64,46 +64,48 @@ bn_partial_stats_kernel(const T* __restrict__ x, const float* __restrict__ shift
     }
 }
 
-// Sum the per-CTA partials of 32 channels with 8 part-lanes (CTA = 256 threads, grid = ceil(C/32)).
-__device__ __forceinline__ void reduce_parts(const float* __restrict__ part, int nparts, int C, int c, int lane8,
+// Sum the per-CTA partials of 32 channels with FL part-lanes (CTA = 32*FL threads, grid = ceil(C/32)).  The loop is
+// latency-bound (one L2 round trip per row), so every thread keeps 8 independent rows (16 loads) in flight and
+// FL = 32 lanes share the rows: <= 3 trips at 592 partials.
+constexpr int FL = 32;
+
+__device__ __forceinline__ void reduce_parts(const float* __restrict__ part, int nparts, int C, int c, int lane_p,
                                              float (*sh)[2][33], float& sa, float& sb) {
-    // 8 independent rows per trip: the loop is latency-bound (one L2 round trip per row when not unrolled,
-    // ~75 dependent trips at 592 partials), so keep 16 loads in flight per thread
     float a = 0.f, b = 0.f;
     if (c < C) {
-        int q = lane8;
-        for (; q + 56 < nparts; q += 64) {
+        int q = lane_p;
+        for (; q + 7 * FL < nparts; q += 8 * FL) {
             float va[8], vb[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                va[u] = part[(size_t)(q + 8 * u) * 2 * C + c];
-                vb[u] = part[(size_t)(q + 8 * u) * 2 * C + C + c];
+                va[u] = part[(size_t)(q + FL * u) * 2 * C + c];
+                vb[u] = part[(size_t)(q + FL * u) * 2 * C + C + c];
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) { a += va[u]; b += vb[u]; }
         }
-        for (; q < nparts; q += 8) {
+        for (; q < nparts; q += FL) {
             a += part[(size_t)q * 2 * C + c];
             b += part[(size_t)q * 2 * C + C + c];
         }
     }
-    sh[lane8][0][threadIdx.x & 31] = a;
-    sh[lane8][1][threadIdx.x & 31] = b;
+    sh[lane_p][0][threadIdx.x & 31] = a;
+    sh[lane_p][1][threadIdx.x & 31] = b;
     __syncthreads();
     sa = 0.f; sb = 0.f;
-    if (lane8 == 0) {
+    if (lane_p == 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { sa += sh[q][0][threadIdx.x & 31]; sb += sh[q][1][threadIdx.x & 31]; }
+        for (int q = 0; q < FL; ++q) { sa += sh[q][0][threadIdx.x & 31]; sb += sh[q][1][threadIdx.x & 31]; }
     }
 }
 
 // ---- stage 2 (forward): batch mean / rstd, running statistics (nn.BatchNorm2d semantics) --------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * FL)
 bn_finalize_stats_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ shift_src,
                          float* __restrict__ save_mean, float* __restrict__ save_rstd,
                          float* __restrict__ running_mean, float* __restrict__ running_var,
                          long long P, int C, float eps, float momentum) {
-    __shared__ float sh[8][2][33];
+    __shared__ float sh[FL][2][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane8 = threadIdx.x >> 5;
     float sa, sb;
     reduce_parts(part, nparts, C, c, lane8, sh, sa, sb);
@@ -168,6 +170,57 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const fl
     }
 }
 
+
+// Leaner stage 3: four channels per thread, FPIX4 pixels in flight (the octet kernel needs 93 registers -> 21 %
+// occupancy in the round-1 ncu capture).
+constexpr int FPIX4 = 4;
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+bn_apply_fwd4_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ mean,
+                     const float* __restrict__ rstd_or_var, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, T* __restrict__ out, long long P, int C, float eps, int relu) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4 = C >> 2;
+    const int cc = (int)(t % c4) * 4;
+    const long long p0 = (t / c4) * FPIX4;
+    if (p0 >= P) return;
+    const float4 m4 = *reinterpret_cast<const float4*>(mean + cc), r4 = *reinterpret_cast<const float4*>(rstd_or_var + cc);
+    const float4 g4 = *reinterpret_cast<const float4*>(gamma + cc), b4 = *reinterpret_cast<const float4*>(beta + cc);
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    float sc[4], sh[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float rs = (MODE == 0) ? r[u] : 1.f / sqrtf(r[u] + eps);
+        sc[u] = rs * g[u];
+        sh[u] = b[u] - m[u] * sc[u];
+    }
+    Vec4<T> v[FPIX4], rv[FPIX4];
+#pragma unroll
+    for (int q = 0; q < FPIX4; ++q)
+        if (p0 + q < P) {
+            v[q].load(x + (p0 + q) * C + cc);
+            if (res != nullptr) rv[q].load(res + (p0 + q) * C + cc);
+        }
+#pragma unroll
+    for (int q = 0; q < FPIX4; ++q) {
+        if (p0 + q >= P) break;
+        float f[4], rf[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+        v[q].get(f);
+        if (res != nullptr) rv[q].get(rf);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            o[u] = fmaf(f[u], sc[u], sh[u]);
+            if (res != nullptr) o[u] += rf[u];
+            if (relu) o[u] = fmaxf(o[u], 0.f);
+        }
+        Vec4<T> w;
+        w.set(o);
+        w.store(out + (p0 + q) * C + cc);
+    }
+}
+
 // ---- backward stage 1: partial sums of dyr = dy * relu'(out) and dyr * xhat ----------------------
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
@@ -217,10 +270,10 @@ bn_partial_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ out, const
 }
 
 // ---- backward stage 2: dbeta = S1, dgamma = S2 ----------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * FL)
 bn_finalize_bwd_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, int C) {
-    __shared__ float sh[8][2][33];
+    __shared__ float sh[FL][2][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane8 = threadIdx.x >> 5;
     float sa, sb;
     reduce_parts(part, nparts, C, c, lane8, sh, sa, sb);
@@ -384,15 +437,17 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
         bn_partial_stats_kernel<bf16><<<chunks, BN_THREADS, smem, st>>>((const bf16*)x, shift, part, P, C, ppc);
     } else { ge_set_error("ge_bn_fwd_train: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_bn_fwd_train(stats)");
-    bn_finalize_stats_kernel<<<ge::cdiv(C, 32), 256, 0, st>>>(part, chunks, shift, save_mean, save_rstd,
+    bn_finalize_stats_kernel<<<ge::cdiv(C, 32), 32 * FL, 0, st>>>(part, chunks, shift, save_mean, save_rstd,
                                                                running_mean, running_var, P, C, eps, momentum);
     GE_CHECK_LAUNCH("ge_bn_fwd_train(finalize)");
+    const unsigned blocks4 = (unsigned)ge::cdivll(ge::cdivll(P, FPIX4) * (C / 4), 256);
+    (void)blocks;
     if (dtype == GE_DTYPE_F32)
-        bn_apply_fwd_kernel<float, 0><<<blocks, 256, 0, st>>>((const float*)x, (const float*)residual, save_mean, save_rstd,
-                                                               gamma, beta, (float*)out, P, C, eps, relu);
+        bn_apply_fwd4_kernel<float, 0><<<blocks4, 256, 0, st>>>((const float*)x, (const float*)residual, save_mean, save_rstd,
+                                                                 gamma, beta, (float*)out, P, C, eps, relu);
     else
-        bn_apply_fwd_kernel<bf16, 0><<<blocks, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, save_mean, save_rstd,
-                                                              gamma, beta, (bf16*)out, P, C, eps, relu);
+        bn_apply_fwd4_kernel<bf16, 0><<<blocks4, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, save_mean, save_rstd,
+                                                                gamma, beta, (bf16*)out, P, C, eps, relu);
     GE_CHECK_LAUNCH("ge_bn_fwd_train(apply)");
     return GE_OK;
 }
@@ -450,7 +505,7 @@ extern "C" int ge_bn_bwd(const void* dy, const void* out, const void* x, const f
         bn_partial_bwd_kernel<bf16><<<chunks, BN_THREADS, smem, st>>>((const bf16*)dy, (const bf16*)out, (const bf16*)x,
                                                                       mean, rstd, part, P, C, ppc, relu);
     GE_CHECK_LAUNCH("ge_bn_bwd(partial)");
-    bn_finalize_bwd_kernel<<<ge::cdiv(C, 32), 256, 0, st>>>(part, chunks, dgamma, dbeta, C);
+    bn_finalize_bwd_kernel<<<ge::cdiv(C, 32), 32 * FL, 0, st>>>(part, chunks, dgamma, dbeta, C);
     GE_CHECK_LAUNCH("ge_bn_bwd(finalize)");
     const float invP = 1.f / (float)P;
     const long long total4 = ge::cdivll(P, BPIX4) * (C / 4);
