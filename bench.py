@@ -170,6 +170,59 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ Sinkhorn iters/s
+def sinkhorn_rates(dev, cpu=True):
+    """BASELINE.json's second metric: Sinkhorn iterations per second (1 iteration = one row + one column
+    normalisation pass, graph_matching.py:659-669) of the fused instance-norm + sinkhorn_rpm(20) + exp kernel on
+    252x252 matrices: one problem (the reference's shape, latency-bound) and 512 independent problems (saturating),
+    CUDA-event timed; beside it the CPU oracle port of the same loop on the host cores."""
+    from graphecho_b200 import functional as GF
+    out = {"metric": "Sinkhorn iters/s (instance-norm + sinkhorn_rpm, 20 iterations, 252x252, slack row/column)"}
+    for tag, batch in (("single_problem", 1), ("batched_512", 512)):
+        M = torch.randn(batch, 252, 252, device=dev)
+        for _ in range(3):
+            GF.sinkhorn_rpm_exp(M, 20, True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            GF.sinkhorn_rpm_exp(M, 20, True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        out[tag] = {"iters_per_s": 20 * batch / (ms / 1e3), "ms_per_call": ms}
+    if cpu:
+        from oracle import graph_ops as G
+        Mc = torch.randn(252, 252)
+        G.sinkhorn_rpm_exp(Mc, 20, True)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            G.sinkhorn_rpm_exp(Mc, 20, True)
+        dt = (time.perf_counter() - t0) / 10
+        out["cpu_port"] = {"iters_per_s": 20 / dt, "ms_per_call": dt * 1e3, "cores": os.cpu_count() or 1}
+    return out
+
+
+def ncu_traffic(entry):
+    """DRAM bytes per call of a C-ABI entry point from the committed `ncu --set full` capture
+    (profiles/r1d_ncu_kernels.json: every kernel of the entry at the [256,256,28,28] bf16 shape), or None."""
+    fam = {"ge_bn_bwd": ("bn_partial_bwd", "bn_finalize_bwd", "bn_apply_bwd"),
+           "ge_bn_fwd_train": ("bn_partial_stats", "bn_finalize_stats", "bn_apply_fwd"),
+           "ge_gn_relu_upsample_bwd": ("gn_relu_up_bwd_reduce", "gn_relu_up_bwd_apply"),
+           "ge_gn_relu_upsample_fwd": ("gn_relu_up_fwd",), "ge_group_stats": ("group_stats",),
+           "ge_knn_graph_nmajor": ("knn_split_nmajor", "knn_tc_kernel"),
+           "ge_mrconv_gather_nmajor_fwd": ("mr_gather_nmajor_fwd",),
+           "ge_mrconv_gather_nmajor_bwd": ("mr_gather_nmajor_bwd_init", "mr_gather_nmajor_bwd_scatter")}.get(entry)
+    try:
+        rows = json.loads((ROOT / "profiles" / "r1d_ncu_kernels.json").read_text())
+    except Exception:
+        return None
+    if not fam:
+        return None
+    tot = sum((r["rd"] + r["wr"]) * 1e6 for r in rows if any(r["kernel"].startswith(f) for f in fam))
+    return tot or None
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(a):
     import torch.distributed as dist
@@ -277,7 +330,10 @@ def run_ours(a):
         r = prof[top]
         ach = r["bytes"] / r["ms"] / 1e6
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": peak_src,
-                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic(top),
+                    "traffic_note": "dram__bytes_read+write of one call at the largest map of the step ([256,256,28,28] bf16, "
+                                    "103 MB), ncu --set full, profiles/r1d_ncu_kernels.json; `achieved` averages all "
+                                    "launches of the step (most maps are smaller and launch-bound)",
                     "launches_per_step": r["calls"], "avg_ms": r["ms"] / r["calls"]}
 
     cpu_baseline = None
@@ -289,6 +345,7 @@ def run_ours(a):
                         "sample": f"2 clips x {a.cpu_sample_frames} frames = {nframes} frames/step, 2 timed steps "
                                   f"after 1 warm-up, {cms:.0f} ms/step, {cpu_model()}"}
 
+    sinkhorn = sinkhorn_rates(dev, cpu=not a.skip_cpu_baseline) if rank == 0 else None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -298,7 +355,7 @@ def run_ours(a):
                            "l2": "per-step working set (activations > 4 GB) exceeds the 126 MB L2; no flush needed",
                            "grad_allreduce_bytes": eng.grads.nbytes, "loss": float(last)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "kernels": kernels}
+                "cpu_baseline": cpu_baseline, "sinkhorn": sinkhorn, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

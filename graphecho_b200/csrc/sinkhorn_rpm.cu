@@ -342,7 +342,7 @@ sinkhorn_rpm_bwd_kernel(const float* __restrict__ M, const float* __restrict__ G
 
 constexpr size_t kSmemCap = 220 * 1024;
 
-int pick_cluster(int N1, int N2, bool bwd, int requested) {
+int pick_cluster(int N1, int N2, bool bwd, int requested, int batch = 1) {
     const int ld = (N2 + 3) & ~3;
     const int cands[5] = {1, 2, 4, 8, 16};
     if (requested > 0) {
@@ -351,6 +351,15 @@ int pick_cluster(int N1, int N2, bool bwd, int requested) {
                 const int R = ge::cdiv(N1, c);
                 return rpm_smem_floats(R, ld, ld, bwd) * sizeof(float) <= kSmemCap ? c : -1;
             }
+        return -1;
+    }
+    // Throughput heuristic for batches that fill the machine anyway: the smallest cluster that holds the matrix
+    // (more problems in flight, fewer DSMEM exchanges per pass).
+    if ((long long)batch * 8 >= 2LL * ge::sm_count()) {
+        for (int c : cands) {
+            const int R = ge::cdiv(N1, c);
+            if (rpm_smem_floats(R, ld, ld, bwd) * sizeof(float) <= kSmemCap) return c;
+        }
         return -1;
     }
     // Latency heuristic: aim for <= 48 rows per CTA, grow further only if capacity demands it.
@@ -409,7 +418,7 @@ extern "C" int ge_sinkhorn_rpm_fwd(const float* M, float* P, float* hist_r, floa
                                    int cluster_size, ge_stream_t stream) {
     GE_REQUIRE(M && P && hist_r && hist_c && stats, GE_ERR_ARG, "ge_sinkhorn_rpm_fwd: null pointer");
     GE_REQUIRE(batch > 0 && N1 > 0 && N2 > 0 && n_iters >= 0, GE_ERR_ARG, "ge_sinkhorn_rpm_fwd: bad dimension");
-    const int cs = pick_cluster(N1, N2, false, cluster_size);
+    const int cs = pick_cluster(N1, N2, false, cluster_size, batch);
     GE_REQUIRE(cs > 0, GE_ERR_CAPACITY,
                "ge_sinkhorn_rpm_fwd: %dx%d does not fit the on-chip cluster layout (cluster_size=%d)", N1, N2, cluster_size);
     const int ld = (N2 + 3) & ~3;
@@ -423,7 +432,7 @@ extern "C" int ge_sinkhorn_rpm_bwd(const float* M, const float* G, const float* 
                                    int apply_instnorm, int cluster_size, ge_stream_t stream) {
     GE_REQUIRE(M && G && hist_r && hist_c && stats && dM, GE_ERR_ARG, "ge_sinkhorn_rpm_bwd: null pointer");
     GE_REQUIRE(batch > 0 && N1 > 0 && N2 > 0 && n_iters >= 0, GE_ERR_ARG, "ge_sinkhorn_rpm_bwd: bad dimension");
-    const int cs = pick_cluster(N1, N2, true, cluster_size);
+    const int cs = pick_cluster(N1, N2, true, cluster_size, batch);
     GE_REQUIRE(cs > 0, GE_ERR_CAPACITY,
                "ge_sinkhorn_rpm_bwd: %dx%d does not fit the on-chip cluster layout (cluster_size=%d)", N1, N2, cluster_size);
     const int ld = (N2 + 3) & ~3;
