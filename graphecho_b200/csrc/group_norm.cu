@@ -31,8 +31,8 @@ __device__ __forceinline__ float group_lane_sum(float v, int cpg) {
 // ---- statistics: mean / rstd of every group, written expanded per channel [N,C] -----------------
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-group_stats_kernel(const T* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd,
-                   int HW, int C, float eps, int cpg) {
+group_stats_kernel(const T* __restrict__ x, const float* __restrict__ pre_bias, float* __restrict__ mean,
+                   float* __restrict__ rstd, float* __restrict__ chan_sum, int HW, int C, float eps, int cpg) {
     extern __shared__ __align__(16) float sm[];      // [nPL][C] sums, [nPL][C] squares, [C] shift
     const int c8 = C >> 3, nPL = GN_THREADS / c8;
     float* ssum = sm;
@@ -72,7 +72,12 @@ group_stats_kernel(const T* __restrict__ x, float* __restrict__ mean, float* __r
     for (int c = tid; c < C; c += GN_THREADS) {      // C % 32 == 0 when cpg > 1: whole warps stay together
         float sa = 0.f, sb = 0.f;
         for (int q = 0; q < nPL; ++q) { sa += ssum[q * C + c]; sb += ssq[q * C + c]; }
-        const float sh = sshift[c];
+        // Statistics of x + pre_bias (a per-channel constant, e.g. the bias of the convolution that produced x,
+        // folded here so that neither the add nor its gradient reduction is a separate pass).  The stored mean is
+        // the EFFECTIVE one, mean(x + b) - b[c]: every consumer normalises the raw x with it.
+        const float pb = pre_bias != nullptr ? pre_bias[c] : 0.f;
+        const float sh = sshift[c] + pb;
+        if (chan_sum != nullptr) chan_sum[(size_t)n * C + c] = fmaf((float)HW, sshift[c], sa);
         float m, var;
         if (cpg == 1) {
             const float md = sa * inv;
@@ -88,6 +93,7 @@ group_stats_kernel(const T* __restrict__ x, float* __restrict__ mean, float* __r
             m = S * ginv;
             var = fmaxf(Q * ginv - m * m, 0.f);
         }
+        m -= pb;
         mean[(size_t)n * C + c] = m;
         rstd[(size_t)n * C + c] = 1.f / sqrtf(var + eps);
     }
@@ -444,8 +450,28 @@ int set_smem_once(K kernel, size_t bytes, size_t& cached, const char* name) {
 }  // namespace
 
 // mean, rstd: fp32 [N,C], the statistics of each group written for every one of its channels.
+namespace {
+int group_stats_impl(const void* x, const float* pre_bias, float* mean, float* rstd, float* chan_sum, int dtype,
+                     int N, int HW, int C, int channels_per_group, float eps, ge_stream_t stream);
+}
+
 extern "C" int ge_group_stats(const void* x, float* mean, float* rstd, int dtype,
                               int N, int HW, int C, int channels_per_group, float eps, ge_stream_t stream) {
+    return group_stats_impl(x, nullptr, mean, rstd, nullptr, dtype, N, HW, C, channels_per_group, eps, stream);
+}
+
+// Statistics of x + pre_bias[c] (pre_bias fp32 [C] or NULL).  mean receives the EFFECTIVE mean (group mean minus
+// pre_bias[c]) so that ge_gn_relu_upsample_fwd/bwd run unchanged on the raw x; chan_sum (fp32 [N,C] or NULL) receives
+// sum_hw x[n,:,c], from which the caller gets the gradient of pre_bias without a pass over the map.
+extern "C" int ge_group_stats_bias(const void* x, const float* pre_bias, float* mean, float* rstd, float* chan_sum,
+                                   int dtype, int N, int HW, int C, int channels_per_group, float eps,
+                                   ge_stream_t stream) {
+    return group_stats_impl(x, pre_bias, mean, rstd, chan_sum, dtype, N, HW, C, channels_per_group, eps, stream);
+}
+
+namespace {
+int group_stats_impl(const void* x, const float* pre_bias, float* mean, float* rstd, float* chan_sum, int dtype,
+                     int N, int HW, int C, int channels_per_group, float eps, ge_stream_t stream) {
     GE_REQUIRE(x && mean && rstd, GE_ERR_ARG, "ge_group_stats: null pointer");
     GE_REQUIRE(N > 0 && HW > 0 && C > 0, GE_ERR_ARG, "ge_group_stats: bad dimension");
     GE_REQUIRE(gn_shape_ok(C, channels_per_group), GE_ERR_SHAPE,
@@ -457,15 +483,16 @@ extern "C" int ge_group_stats(const void* x, float* mean, float* rstd, int dtype
     if (dtype == GE_DTYPE_F32) {
         int rc = set_smem_once(group_stats_kernel<float>, smem, c0, "ge_group_stats(attr)");
         if (rc) return rc;
-        group_stats_kernel<float><<<N, GN_THREADS, smem, st>>>((const float*)x, mean, rstd, HW, C, eps, channels_per_group);
+        group_stats_kernel<float><<<N, GN_THREADS, smem, st>>>((const float*)x, pre_bias, mean, rstd, chan_sum, HW, C, eps, channels_per_group);
     } else if (dtype == GE_DTYPE_BF16) {
         int rc = set_smem_once(group_stats_kernel<bf16>, smem, c1, "ge_group_stats(attr)");
         if (rc) return rc;
-        group_stats_kernel<bf16><<<N, GN_THREADS, smem, st>>>((const bf16*)x, mean, rstd, HW, C, eps, channels_per_group);
+        group_stats_kernel<bf16><<<N, GN_THREADS, smem, st>>>((const bf16*)x, pre_bias, mean, rstd, chan_sum, HW, C, eps, channels_per_group);
     } else { ge_set_error("ge_group_stats: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_group_stats");
     return GE_OK;
 }
+}  // namespace
 
 extern "C" int ge_gn_relu_upsample_fwd(const void* x, const float* mean, const float* rstd,
                                        const float* gamma, const float* beta, void* out, int dtype,

@@ -402,8 +402,8 @@ def upsample_bilinear(x, size):
 
 class _GnReluUpsample(Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, size, eps, groups):
-        _need_cuda(x, gamma, beta)
+    def forward(ctx, x, gamma, beta, size, eps, groups, pre_bias=None):
+        _need_cuda(x, gamma, beta, pre_bias)
         xc = _nhwc_view(x)
         N, C, h, w = xc.shape
         H, W = size
@@ -413,20 +413,28 @@ class _GnReluUpsample(Function):
         rstd = torch.empty_like(mean)
         code = _dtype_code(xc)
         es = xc.element_size()
-        call("ge_group_stats", ptr(xc), ptr(mean), ptr(rstd), code, N, h * w, C, cpg, c_float(eps), stream(),
-             work=(N * C * h * w * es, 3 * N * C * h * w))
+        csum = None
+        if pre_bias is None:
+            call("ge_group_stats", ptr(xc), ptr(mean), ptr(rstd), code, N, h * w, C, cpg, c_float(eps), stream(),
+                 work=(N * C * h * w * es, 3 * N * C * h * w))
+        else:
+            # statistics of x + pre_bias; `mean` is the effective mean (group mean - pre_bias[c]), so everything
+            # downstream normalises the raw x
+            csum = torch.empty_like(mean)
+            call("ge_group_stats_bias", ptr(xc), ptr(_f32c(pre_bias)), ptr(mean), ptr(rstd), ptr(csum), code,
+                 N, h * w, C, cpg, c_float(eps), stream(), work=(N * C * h * w * es, 3 * N * C * h * w))
         out = torch.empty((N, C, H, W), device=x.device, dtype=xc.dtype, memory_format=torch.channels_last)
         call("ge_gn_relu_upsample_fwd", ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(out), code,
              N, h, w, H, W, C, stream(), work=(N * C * es * (h * w + H * W), 12 * N * C * H * W))
-        ctx.save_for_backward(xc, mean, rstd, g, b)
-        ctx.cfg = (N, C, h, w, H, W, cpg, gamma.dtype, beta.dtype)
+        ctx.save_for_backward(xc, mean, rstd, g, b, csum)
+        ctx.cfg = (N, C, h, w, H, W, cpg, gamma.dtype, beta.dtype, None if pre_bias is None else pre_bias.dtype)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        xc, mean, rstd, g, b = ctx.saved_tensors
-        N, C, h, w, H, W, cpg, gdt, bdt = ctx.cfg
+        xc, mean, rstd, g, b, csum = ctx.saved_tensors
+        N, C, h, w, H, W, cpg, gdt, bdt, pdt = ctx.cfg
         d = _nhwc_view(dout.to(xc.dtype))
         es = xc.element_size()
         if (h, w) != (H, W):
@@ -440,7 +448,14 @@ class _GnReluUpsample(Function):
         call("ge_gn_relu_upsample_bwd", ptr(d), ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(None),
              ptr(S[0]), ptr(S[1]), ptr(S[2]), ptr(S[3]), ptr(dx), _dtype_code(xc), N, h, w, h, w, C, cpg, stream(),
              work=(N * C * es * 4 * h * w, 20 * N * C * h * w))
-        return dx, S[1].sum(0).to(gdt), S[0].sum(0).to(bdt), None, None, None
+        dpb = None
+        if csum is not None:
+            # d/d pre_bias = sum_{n,hw} dx, in closed form from the [N,C] arrays of the two kernels (no pass over dx):
+            # sum_hw dx = rstd*(gamma*S1 - HW*A1 - A2*sum_hw xhat),  sum_hw xhat = rstd*(sum_hw x - HW*mean_eff)
+            hw = float(h * w)
+            sum_xhat = rstd * (csum - hw * mean)
+            dpb = (rstd * (g * S[0] - hw * S[2] - S[3] * sum_xhat)).sum(0).to(pdt)
+        return dx, S[1].sum(0).to(gdt), S[0].sum(0).to(bdt), None, None, None, dpb
 
 
 def gn_relu_upsample(x, gamma, beta, size, eps=1e-5, groups=None):
@@ -450,9 +465,11 @@ def gn_relu_upsample(x, gamma, beta, size, eps=1e-5, groups=None):
     return _GnReluUpsample.apply(x, gamma, beta, (int(size[0]), int(size[1])), float(eps), groups)
 
 
-def gn_relu(x, gamma, beta, groups, eps=1e-5):
-    """relu(GroupNorm(groups, C)(x)) on an NHWC map (Discriminator towers, fpnseg.py:455-466)."""
-    return _GnReluUpsample.apply(x, gamma, beta, (int(x.shape[2]), int(x.shape[3])), float(eps), int(groups))
+def gn_relu(x, gamma, beta, groups, eps=1e-5, pre_bias=None):
+    """relu(GroupNorm(groups, C)(x + pre_bias)) on an NHWC map (Discriminator towers, fpnseg.py:455-466).
+    `pre_bias` [C] is the bias of the convolution that produced x: folded into the statistics kernel, so the
+    convolution runs without its bias-add pass and autograd without the bias-gradient reduction pass."""
+    return _GnReluUpsample.apply(x, gamma, beta, (int(x.shape[2]), int(x.shape[3])), float(eps), int(groups), pre_bias)
 
 
 class _BnAct(Function):

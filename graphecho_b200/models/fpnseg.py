@@ -246,7 +246,9 @@ class Discriminator(nn.Module):
         mods = list(self.dis_tower)
         for i in range(0, len(mods), 3):
             conv, gn = mods[i], mods[i + 1]
-            x = GF.gn_relu(conv(x), gn.weight, gn.bias, gn.num_groups, gn.eps)
+            # conv bias folded into the GroupNorm kernels: no separate bias-add / bias-gradient passes over the map
+            y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+            x = GF.gn_relu(y, gn.weight, gn.bias, gn.num_groups, gn.eps, pre_bias=conv.bias)
         return self.cls_logits(x).float()
 
     def forward_joint(self, feature_all, n_source):

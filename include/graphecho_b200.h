@@ -155,6 +155,13 @@ int ge_upsample_bwd(const void* dout, void* dtop, int dtype,
  *      Group statistics over HW x channels_per_group, written per channel: mean, rstd fp32 [N,C]. */
 int ge_group_stats(const void* x, float* mean, float* rstd, int dtype,
                    int N, int HW, int C, int channels_per_group, float eps, ge_stream_t stream);
+/* Same statistics for x + pre_bias[c] (the bias of the convolution that produced x, folded into the norm so that
+ * neither the add nor its gradient reduction is a separate pass).  mean receives the EFFECTIVE mean
+ * (group mean - pre_bias[c]): ge_gn_relu_upsample_fwd/bwd then run unchanged on the raw x.  chan_sum [N,C] (or NULL)
+ * receives sum_hw x[n,:,c]; the gradient of pre_bias follows from it and the backward's S/A arrays. */
+int ge_group_stats_bias(const void* x, const float* pre_bias, float* mean, float* rstd, float* chan_sum,
+                        int dtype, int N, int HW, int C, int channels_per_group, float eps,
+                        ge_stream_t stream);
 /* out [N,H,W,C] = bilinear_up(relu((x-mean)*rstd*gamma+beta)); x [N,h,w,C]; (h,w)==(H,W) = no up-sampling. */
 int ge_gn_relu_upsample_fwd(const void* x, const float* mean, const float* rstd,
                             const float* gamma, const float* beta, void* out, int dtype,

@@ -504,3 +504,31 @@ def test_bn_act_train_and_eval(dev, C, hw, res, relu, dtype):
         ref_e = torch.relu(y) if relu else y
         out_e = GF.bn_act(_cl(x, dev, dtype), our_bn, residual=None if not res else _cl(r, dev, dtype), relu=relu)
     close(out_e, ref_e, rtol=2e-2 if lo else 1e-4, atol=3e-2 if lo else 2e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gn_relu_with_folded_conv_bias(dev, dtype):
+    """relu(GroupNorm(32)(x + b)) with b folded into the statistics kernel == the plain composition, including the
+    closed-form gradient of b (no pass over dx)."""
+    torch.manual_seed(4)
+    N, C, H = 3, 64, 9
+    x = (torch.randn(N, C, H, H) * 2).to(dtype)
+    bias = torch.randn(C)
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C)
+    xo, bo = x.float().clone().requires_grad_(), bias.clone().requires_grad_()
+    go, beo = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    ref = torch.relu(F.group_norm(xo + bo.view(1, C, 1, 1), 32, go, beo, 1e-5))
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_()
+    bd = bias.to(dev).requires_grad_()
+    gd, bed = gamma.to(dev).requires_grad_(), beta.to(dev).requires_grad_()
+    out = GF.gn_relu(xd, gd, bed, 32, 1e-5, pre_bias=bd)
+    tol = dict(rtol=2e-4, atol=2e-5) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    close(out.float(), ref, **tol)
+    (out.float() * W.to(dev)).sum().backward()
+    gt = dict(rtol=2e-3, atol=2e-4) if dtype == torch.float32 else dict(rtol=5e-2, atol=8e-2)
+    close(xd.grad.float(), xo.grad, **gt)
+    close(bd.grad, bo.grad, **gt)
+    close(gd.grad, go.grad, **gt)
+    close(bed.grad, beo.grad, **gt)
