@@ -47,6 +47,8 @@ _SIGNATURES = {
     "ge_upsample_add_fwd": (c_int, [P, P, P, I, I, I, I, I, I, I, P]),
     "ge_upsample_bwd": (c_int, [P, P, I, I, I, I, I, I, I, P]),
     "ge_group_stats": (c_int, [P, P, P, I, I, I, I, I, F, P]),
+    "ge_maxpool3s2_fwd": (c_int, [P, P, P, I, I, I, I, I, P]),
+    "ge_maxpool3s2_bwd": (c_int, [P, P, P, I, I, I, I, I, P]),
     "ge_group_stats_bias": (c_int, [P, P, P, P, P, I, I, I, I, I, F, P]),
     "ge_gn_relu_upsample_fwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, I, P]),
     "ge_gn_relu_upsample_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P]),

@@ -472,6 +472,42 @@ def gn_relu(x, gamma, beta, groups, eps=1e-5, pre_bias=None):
     return _GnReluUpsample.apply(x, gamma, beta, (int(x.shape[2]), int(x.shape[3])), float(eps), int(groups), pre_bias)
 
 
+class _MaxPool3s2(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        xc = _nhwc_view(x)
+        N, C, H, W = xc.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        out = torch.empty((N, C, Ho, Wo), device=x.device, dtype=xc.dtype, memory_format=torch.channels_last)
+        arg = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.uint8)
+        es = xc.element_size()
+        call("ge_maxpool3s2_fwd", ptr(xc), ptr(out), ptr(arg), _dtype_code(xc), N, H, W, C, stream(),
+             work=(N * C * (es * H * W + (es + 1) * Ho * Wo), 9 * N * C * Ho * Wo))
+        ctx.save_for_backward(arg)
+        ctx.cfg = (N, C, H, W, xc.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (arg,) = ctx.saved_tensors
+        N, C, H, W, dt = ctx.cfg
+        d = _nhwc_view(dout.to(dt))
+        dx = torch.empty((N, C, H, W), device=d.device, dtype=dt, memory_format=torch.channels_last)
+        es = d.element_size()
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        call("ge_maxpool3s2_bwd", ptr(d), ptr(arg), ptr(dx), _dtype_code(d), N, H, W, C, stream(),
+             work=(N * C * (es * H * W + (es + 1) * Ho * Wo), 4 * N * C * H * W))
+        return dx
+
+
+def maxpool3s2(x):
+    """nn.MaxPool2d(3, 2, 1) on an NHWC map (ResNet stem, fpnseg.py:232): one pass forward, a deterministic gather
+    backward."""
+    return _MaxPool3s2.apply(x)
+
+
 class _BnAct(Function):
     """Training-mode fused BatchNorm2d (+ residual) (+ ReLU) on an NHWC map."""
 

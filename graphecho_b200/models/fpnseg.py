@@ -117,7 +117,8 @@ class ResNet(nn.Module):
                 m.bias.data.zero_()
 
     def forward(self, x):
-        x = self.maxpool(GF.bn_act(self.conv1(x), self.bn1, relu=True))
+        x = GF.bn_act(self.conv1(x), self.bn1, relu=True)
+        x = GF.maxpool3s2(x) if x.shape[1] % 8 == 0 else self.maxpool(x)
         feats = [x]
         for stage in (self.layer1, self.layer2, self.layer3, self.layer4):
             x = stage(x)

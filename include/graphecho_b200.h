@@ -211,6 +211,15 @@ int ge_spectral_bipartition_max_points(void);
 int ge_spectral_bipartition(const float* pts, unsigned char* keep, int n, int d, int n_neighbors,
                             int iterations, ge_stream_t stream);
 
+/* ---- stem max pooling -----------------------------------------------------------------------
+ * nn.MaxPool2d(3, 2, 1) of the ResNet stem (models/fpnseg.py:232, 254) on an NHWC map in `dtype`:
+ * x [N,H,W,C] -> out [N,Ho,Wo,C], Ho = (H-1)/2+1; arg uint8 [N,Ho,Wo,C] = selected window tap (first maximum).
+ * Backward is a deterministic gather (no atomics): dx [N,H,W,C] overwritten. */
+int ge_maxpool3s2_fwd(const void* x, void* out, unsigned char* arg, int dtype,
+                      int N, int H, int W, int C, ge_stream_t stream);
+int ge_maxpool3s2_bwd(const void* dout, const unsigned char* arg, void* dx, int dtype,
+                      int N, int H, int W, int C, ge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -532,3 +532,21 @@ def test_gn_relu_with_folded_conv_bias(dev, dtype):
     close(bd.grad, bo.grad, **gt)
     close(gd.grad, go.grad, **gt)
     close(bed.grad, beo.grad, **gt)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("hw", [(56, 56), (9, 14)])
+def test_maxpool3s2_matches_torch(dev, dtype, hw):
+    torch.manual_seed(2)
+    x = torch.randn(3, 16, *hw).to(dtype)
+    x[0, :, 2:5, 2:5] = 1.5                                     # ties inside windows: first maximum wins
+    xo = x.float().clone().requires_grad_()
+    ref = F.max_pool2d(xo, 3, 2, 1)
+    Wt = torch.randn_like(ref).to(dtype).float()
+    (ref * Wt).sum().backward()
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_()
+    out = GF.maxpool3s2(xd)
+    assert out.shape == ref.shape and out.dtype == dtype
+    close(out.float(), ref, rtol=0, atol=0)
+    (out.float() * Wt.to(dev)).sum().backward()
+    close(xd.grad.float(), xo.grad, rtol=1e-6 if dtype == torch.float32 else 1e-2, atol=1e-6 if dtype == torch.float32 else 2e-2)
