@@ -8,7 +8,8 @@
 //   backward: partial sums of dy*relu' and dy*relu'*xhat (3 reads) -> finalize (dgamma, dbeta) ->
 //             apply (3 reads, 1-2 writes)
 // Statistics are reduced in two deterministic stages (per-CTA partials in a workspace, then one small
-// CTA), never with atomics.  Each thread moves 8 consecutive channels (one 128-bit access in bf16).
+// CTA), never with atomics.  The statistics kernels move 8 consecutive channels per thread (one 128-bit access in
+// bf16), the apply kernels 4 (half the registers, twice the occupancy).
 // HBM-bound; algorithmic bytes per element (bf16): forward 6 (+2 with a residual), backward 14 (+2).
 #include "common.cuh"
 #include "../../include/graphecho_b200.h"
@@ -124,55 +125,10 @@ bn_finalize_stats_kernel(const float* __restrict__ part, int nparts, const float
 }
 
 // ---- stage 3 (forward): out = act( x*sc + sh (+ residual) ) --------------------------------------
-// MODE 0: training (sc/sh from save_mean/save_rstd); MODE 1: inference (from running stats, `rstd` = var)
-// A thread owns one channel octet of PIX consecutive pixels: the per-channel constants are loaded once
-// and PIX independent 128-bit loads are in flight before the first use.
-constexpr int PIX = 4;
-
-template <typename T, int MODE>
-__global__ void __launch_bounds__(256)
-bn_apply_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ mean,
-                    const float* __restrict__ rstd_or_var, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, T* __restrict__ out, long long P, int C, float eps, int relu) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c8 = C >> 3;
-    const int cc = (int)(t % c8) * 8;
-    const long long p0 = (t / c8) * PIX;
-    if (p0 >= P) return;
-    float m[8], r[8], g[8], b[8], sc[8], sh[8];
-    load8f(mean + cc, m); load8f(rstd_or_var + cc, r); load8f(gamma + cc, g); load8f(beta + cc, b);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const float rs = (MODE == 0) ? r[u] : 1.f / sqrtf(r[u] + eps);
-        sc[u] = rs * g[u];
-        sh[u] = b[u] - m[u] * sc[u];
-    }
-    float v[PIX][8], rv[PIX][8];
-#pragma unroll
-    for (int q = 0; q < PIX; ++q)
-        if (p0 + q < P) load8<T>(x + (p0 + q) * C + cc, v[q]);
-    if (res != nullptr) {
-#pragma unroll
-        for (int q = 0; q < PIX; ++q)
-            if (p0 + q < P) load8<T>(res + (p0 + q) * C + cc, rv[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < PIX; ++q) {
-        if (p0 + q >= P) break;
-        float o[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            o[u] = fmaf(v[q][u], sc[u], sh[u]);
-            if (res != nullptr) o[u] += rv[q][u];
-            if (relu) o[u] = fmaxf(o[u], 0.f);
-        }
-        store8<T>(out + (p0 + q) * C + cc, o);
-    }
-}
-
-
-// Leaner stage 3: four channels per thread, FPIX4 pixels in flight (the octet kernel needs 93 registers -> 21 %
-// occupancy in the round-1 ncu capture).
+// MODE 0: training (sc/sh from save_mean/save_rstd); MODE 1: inference (from running stats, `rstd` = var).
+// A thread owns FOUR channels (one 64-bit bf16 access) of FPIX4 consecutive pixels: the per-channel constants are
+// loaded once and FPIX4 independent loads are in flight before the first use (the first version moved 8 channels per
+// thread at 93 registers -> 21 % occupancy in the round-1 ncu capture).
 constexpr int FPIX4 = 4;
 
 template <typename T, int MODE>
@@ -283,58 +239,9 @@ bn_finalize_bwd_kernel(const float* __restrict__ part, int nparts, float* __rest
 }
 
 // ---- backward stage 3: dx = rstd*gamma*(dyr - S1/P - xhat*S2/P);  dres = dyr ------------------------
-constexpr int BPIX = 2;   // three input streams per pixel: keep the register footprint under 128
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-bn_apply_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ out, const T* __restrict__ x,
-                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ gamma, const float* __restrict__ dgamma,
-                    const float* __restrict__ dbeta, T* __restrict__ dx, T* __restrict__ dres,
-                    long long P, int C, float invP, int relu) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c8 = C >> 3;
-    const int cc = (int)(t % c8) * 8;
-    const long long p0 = (t / c8) * BPIX;
-    if (p0 >= P) return;
-    float m[8], r[8], g[8], s1[8], s2[8], k0[8], k1[8], k2[8];
-    load8f(mean + cc, m); load8f(rstd + cc, r); load8f(gamma + cc, g);
-    load8f(dbeta + cc, s1); load8f(dgamma + cc, s2);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {       // dx = k0*dyr - k1 - xhat*k2
-        k0[u] = r[u] * g[u];
-        k1[u] = k0[u] * s1[u] * invP;
-        k2[u] = k0[u] * s2[u] * invP;
-    }
-    float gv[BPIX][8], xv[BPIX][8], ov[BPIX][8];
-#pragma unroll
-    for (int q = 0; q < BPIX; ++q)
-        if (p0 + q < P) { load8<T>(dy + (p0 + q) * C + cc, gv[q]); load8<T>(x + (p0 + q) * C + cc, xv[q]); }
-    if (relu) {
-#pragma unroll
-        for (int q = 0; q < BPIX; ++q)
-            if (p0 + q < P) load8<T>(out + (p0 + q) * C + cc, ov[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < BPIX; ++q) {
-        if (p0 + q >= P) break;
-        float o[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float gq = (relu && !(ov[q][u] > 0.f)) ? 0.f : gv[q][u];
-            gv[q][u] = gq;
-            const float xh = (xv[q][u] - m[u]) * r[u];
-            o[u] = k0[u] * gq - k1[u] - xh * k2[u];
-        }
-        if (dres != nullptr) store8<T>(dres + (p0 + q) * C + cc, gv[q]);
-        store8<T>(dx + (p0 + q) * C + cc, o);
-    }
-}
-
-
-// Leaner backward stage 3: FOUR channels per thread (one 64-bit bf16 access) of BPIX4 consecutive pixels -- about
-// half the live state of the octet kernel above (111 registers, 20 % occupancy, 44 % of DRAM peak in the round-1
-// ncu capture), so twice as many loads are in flight per SM.
+// FOUR channels per thread (one 64-bit bf16 access) of BPIX4 consecutive pixels -- about half the live state of the
+// first, 8-channel version (111 registers, 20 % occupancy, 44 % of DRAM peak in the round-1 ncu capture), so twice
+// as many loads are in flight per SM.
 constexpr int BPIX4 = 4;
 
 template <typename T>
@@ -426,8 +333,6 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
     // shift = running mean when tracked (close to the batch mean), else beta-free zero shift via gamma-less trick
     const float* shift = running_mean != nullptr ? running_mean : save_mean;
     if (running_mean == nullptr) GE_CUDA(cudaMemsetAsync(save_mean, 0, (size_t)C * sizeof(float), st), "ge_bn_fwd_train(memset)");
-    const long long total8 = ge::cdivll(P, PIX) * (C / 8);
-    const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
     static size_t c0 = 0, c1 = 0;
     if (dtype == GE_DTYPE_F32) {
         if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(bn_partial_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_fwd_train(attr)"); c0 = smem; }
@@ -441,7 +346,6 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
                                                                running_mean, running_var, P, C, eps, momentum);
     GE_CHECK_LAUNCH("ge_bn_fwd_train(finalize)");
     const unsigned blocks4 = (unsigned)ge::cdivll(ge::cdivll(P, FPIX4) * (C / 4), 256);
-    (void)blocks;
     if (dtype == GE_DTYPE_F32)
         bn_apply_fwd4_kernel<float, 0><<<blocks4, 256, 0, st>>>((const float*)x, (const float*)residual, save_mean, save_rstd,
                                                                  gamma, beta, (float*)out, P, C, eps, relu);
@@ -459,14 +363,13 @@ extern "C" int ge_bn_fwd_eval(const void* x, const void* residual, const float* 
     GE_REQUIRE(P > 0 && C > 0, GE_ERR_ARG, "ge_bn_fwd_eval: bad dimension");
     GE_REQUIRE(C % 8 == 0, GE_ERR_SHAPE, "ge_bn_fwd_eval: C=%d must be a multiple of 8", C);
     cudaStream_t st = (cudaStream_t)stream;
-    const long long total8 = ge::cdivll(P, PIX) * (C / 8);
-    const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
+    const unsigned blocks4 = (unsigned)ge::cdivll(ge::cdivll(P, FPIX4) * (C / 4), 256);
     if (dtype == GE_DTYPE_F32)
-        bn_apply_fwd_kernel<float, 1><<<blocks, 256, 0, st>>>((const float*)x, (const float*)residual, running_mean, running_var,
-                                                               gamma, beta, (float*)out, P, C, eps, relu);
+        bn_apply_fwd4_kernel<float, 1><<<blocks4, 256, 0, st>>>((const float*)x, (const float*)residual, running_mean, running_var,
+                                                                 gamma, beta, (float*)out, P, C, eps, relu);
     else if (dtype == GE_DTYPE_BF16)
-        bn_apply_fwd_kernel<bf16, 1><<<blocks, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, running_mean, running_var,
-                                                              gamma, beta, (bf16*)out, P, C, eps, relu);
+        bn_apply_fwd4_kernel<bf16, 1><<<blocks4, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, running_mean, running_var,
+                                                                gamma, beta, (bf16*)out, P, C, eps, relu);
     else { ge_set_error("ge_bn_fwd_eval: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_bn_fwd_eval");
     return GE_OK;
@@ -489,8 +392,6 @@ extern "C" int ge_bn_bwd(const void* dy, const void* out, const void* x, const f
     const long long ppc = ge::cdivll(P, chunks);
     const size_t smem = bn_smem(C);
     float* part = static_cast<float*>(workspace);
-    const long long total8 = ge::cdivll(P, BPIX) * (C / 8);
-    const unsigned blocks = (unsigned)ge::cdivll(total8, 256);
     static size_t c0 = 0, c1 = 0;
     const float* rstd = rstd_or_var;
     if (dtype == GE_DTYPE_F32) {
@@ -510,7 +411,6 @@ extern "C" int ge_bn_bwd(const void* dy, const void* out, const void* x, const f
     const float invP = 1.f / (float)P;
     const long long total4 = ge::cdivll(P, BPIX4) * (C / 4);
     const unsigned blocks4 = (unsigned)ge::cdivll(total4, 256);
-    (void)blocks;
     if (dtype == GE_DTYPE_F32)
         bn_apply_bwd4_kernel<float><<<blocks4, 256, 0, st>>>((const float*)dy, (const float*)out, (const float*)x, mean, rstd,
             gamma, dgamma, dbeta, (float*)dx, (float*)dres, P, C, invP, relu);

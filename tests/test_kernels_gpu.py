@@ -455,6 +455,24 @@ def test_spectral_bipartition_kernel_matches_dense_route(dev):
     assert min(agree) > 0.97, agree
 
 
+def test_spectral_bipartition_large_kernel_matches_dense_route(dev):
+    """192 < n <= 512 points: the block-wise / bit-matrix kernel (class banks of a 256-frame step have 200-450
+    nodes) against the dense eigh route."""
+    from graphecho_b200 import _cabi
+    from graphecho_b200.spectral import spectral_bipartition
+    assert _cabi.lib().ge_spectral_bipartition_max_points() == 512
+    agree = []
+    for seed, n in enumerate((193, 260, 333, 448, 511)):
+        g = torch.Generator().manual_seed(100 + seed)
+        a = torch.randn(n, 256, generator=g)
+        a[: n // 3] += 1.5 * torch.randn(1, 256, generator=g)
+        pts = torch.cat([torch.randn(1, 256, generator=g), a])
+        ref = spectral_bipartition(pts, n // 2)                         # CPU: dense route
+        out = spectral_bipartition(pts.to(dev), n // 2).cpu()
+        agree.append((out == ref).float().mean().item())
+    assert min(agree) > 0.97, agree
+
+
 # ---------------------------------------------------------------------------------------- fused BatchNorm
 @pytest.mark.parametrize("C,hw,res,relu,dtype", [(64, 28, False, True, torch.float32), (256, 14, True, True, torch.float32),
                                                  (2048, 4, True, True, torch.float32), (512, 7, False, False, torch.float32),
