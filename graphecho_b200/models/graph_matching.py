@@ -380,9 +380,12 @@ class GModule(nn.Module):
             if len(bs) > k and self.with_cluster_update:
                 keep = self._bipartition(torch.cat([bank[cls][None, :], bs]))
                 # mean of the kept rows without a boolean gather (bs[keep] would synchronise the host with the
-                # clustering kernel); an empty cluster gives 0/0 = NaN exactly like the reference's mean of nothing
+                # clustering kernel).  If the seed ends up alone in its cluster (possible while the bank is still
+                # far from the features) the reference takes the mean of nothing = NaN and poisons the bank for the
+                # rest of training; here such a step falls back to the plain class mean instead.
                 w = keep.to(bs.dtype)
-                bs = (bs * w[:, None]).sum(0) / w.sum()
+                cnt = w.sum()
+                bs = torch.where(cnt > 0, (bs * w[:, None]).sum(0) / cnt.clamp_min(1.0), bs.mean(0))
             else:
                 bs = bs.mean(0)
             mom = F.cosine_similarity(bs.unsqueeze(0), bank[cls].unsqueeze(0))
