@@ -46,3 +46,31 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.ge_sinkhorn_rpm_cluster_size(250, 250, 0) == 8
     assert lib.ge_sinkhorn_rpm_cluster_size(6, 6, 0) == 1
     assert lib.ge_sinkhorn_rpm_cluster_size(4000, 4000, 0) == -1
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    lib = _cabi.lib()
+    assert lib.ge_knn_graph_set_path(7) < 0 and "path" in _cabi.last_error()
+    assert lib.ge_knn_graph_set_path(0) == 0
+    # workspace covers both the fp32 FFMA layout and the (larger) fp16 hi/lo split of the tcgen05 path
+    ffma = 4 * (2 * 256 * (784 + 784) + 2 * (784 + 784))
+    assert lib.ge_knn_graph_workspace_bytes(2, 256, 784, 784) >= ffma
+    assert lib.ge_knn_graph_workspace_bytes(0, 256, 784, 784) == 0
+    assert lib.ge_knn_graph_nmajor_supported(2, 256, 64, 64, 9, 1) == 0          # small graphs: FFMA route only
+    assert lib.ge_knn_graph_nmajor_supported(2, 256, 784, 784, 9, 1) in (0, 1)   # 1 only where the driver is present
+    assert lib.ge_maxpool3s2_fwd(None, None, None, 0, 1, 8, 8, 8, None) < 0 and "null" in _cabi.last_error()
+    assert lib.ge_mrconv_gather_nmajor_fwd(None, None, None, None, None, 0, 1, 8, 4, 4, 3, None) < 0
+    assert lib.ge_group_stats_bias(None, None, None, None, None, 0, 1, 4, 8, 1, 1e-5, None) < 0
+    assert lib.ge_spectral_bipartition_max_points() == 512
+
+
+def test_new_wrappers_reject_cpu_tensors():
+    from graphecho_b200 import functional as GF
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GF.knn_graph_nmajor(torch.randn(1, 128, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GF.mr_gather_nmajor(torch.randn(1, 16, 8), torch.zeros(1, 16, 3, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GF.maxpool3s2(torch.randn(1, 8, 6, 6))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GF.gn_relu(torch.randn(1, 32, 4, 4), torch.ones(32), torch.zeros(32), 4, pre_bias=torch.zeros(32))
