@@ -37,3 +37,33 @@ def test_synthetic_generators():
     assert [t.shape[-1] for t in p] == [28, 14, 7, 4]
     p = synth.pyramid(2, 256)
     assert [t.shape[-1] for t in p] == [64, 32, 16, 8]
+
+
+def test_fp16_hi_lo_split_inner_product_is_fp32_accurate():
+    """Arithmetic model of the tcgen05 k-NN kernel (csrc/knn_tc.cu), emulated on the CPU: every normalised value
+    is split as v = hi + lo * 2^-11 with hi = fp16(v), lo = fp16((v - hi) * 2^11); products of fp16 values are exact
+    in fp32, the tensor core accumulates D1 = sum hi.hi' and D2 = sum (lo.hi' + hi.lo') in fp32, and
+    x.y = D1 + 2^-11 * D2.  The error against the exact inner product must be at the level of a plain fp32 dot
+    product (that is why k-NN indices match the fp32 reference except between candidates < 2e-6 apart)."""
+    torch.manual_seed(0)
+    C, n = 256, 2000
+    x = torch.nn.functional.normalize(torch.randn(n, C, dtype=torch.float64), dim=1).float()
+    y = torch.nn.functional.normalize(torch.randn(n, C, dtype=torch.float64), dim=1).float()
+
+    def split(v):
+        hi = v.half()
+        lo = ((v - hi.float()) * 2048.0).half()
+        return hi.float(), lo.float()
+
+    xh, xl = split(x)
+    yh, yl = split(y)
+    # the split reconstructs v to ~2^-22 relative
+    assert ((xh + xl / 2048.0) - x).abs().max() <= 2.0 ** -21 * x.abs().max()
+    d1 = (xh * yh).sum(1)
+    d2 = (xl * yh).sum(1) + (xh * yl).sum(1)
+    ip = d1 + d2 / 2048.0
+    truth = (x.double() * y.double()).sum(1)
+    err_split = (ip.double() - truth).abs()
+    err_fp32 = ((x * y).sum(1).double() - truth).abs()
+    assert err_split.max() < 1e-7                       # distances are 2 - 2*ip: well inside the 2e-6 near-tie window
+    assert err_split.mean() < 3 * err_fp32.mean() + 1e-9
