@@ -109,7 +109,7 @@ def test_training_makes_progress_and_updates_every_module(dev):
     clips, masks = make_batch(cfg, n_clips=2, frames=4)
     fs, ft, shape = split_streams(clips.to(dev))
     seg = []
-    for _ in range(8):
+    for _ in range(12):
         total, losses = eng.train_step(fs, masks.to(dev), ft, shape)
         seg.append(float(losses["seg_loss"]))
         assert all(torch.isfinite(v) for v in losses.values()), losses
