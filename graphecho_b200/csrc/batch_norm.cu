@@ -5,12 +5,20 @@
 // passes (/root/reference/models/fpnseg.py:192-212 Bottleneck.forward, :251-255 stem, :27-142 VGG16
 // blocks): 8 tensor passes forward and 8 backward per residual block output.  Here:
 //   forward : partial statistics (1 read) -> finalize (+ running-stat update) -> apply (1-2 reads, 1 write)
-//   backward: partial sums of dy*relu' and dy*relu'*xhat (3 reads) -> finalize (dgamma, dbeta) ->
-//             apply (3 reads, 1-2 writes)
+//   backward: partial sums of dy*relu' and dy*relu'*xhat (2 reads) -> finalize (dgamma, dbeta) ->
+//             apply (2 reads, 1-2 writes)
 // Statistics are reduced in two deterministic stages (per-CTA partials in a workspace, then one small
 // CTA), never with atomics.  The statistics kernels move 8 consecutive channels per thread (one 128-bit access in
 // bf16), the apply kernels 4 (half the registers, twice the occupancy).
-// HBM-bound; algorithmic bytes per element (bf16): forward 6 (+2 with a residual), backward 14 (+2).
+// HBM-bound.  Compulsory bytes per element (bf16): forward 4 (+2 with a residual), backward 8 (+2 with a residual
+// gradient); the kernels move forward 6 (+2) and backward 10.25 (+2): the ReLU mask is a 1-bit-per-element side
+// output of the forward, so the backward never re-reads `out`.
+//
+// SEGMENTS (per-domain statistics): the reference trainer runs the network on the source batch and on the target
+// batch in two separate train-mode calls (train_cardiac_uda.py:225, 234), so every BatchNorm normalises each domain
+// with its own batch statistics and updates its running statistics twice per step.  Here both domains travel as ONE
+// [source | target] batch through the convolutions; `P_split` (pixels of the first segment; 0 = one segment) makes
+// the statistics, the running-stat updates (source first, then target) and the backward sums per segment.
 #include "common.cuh"
 #include "../../include/graphecho_b200.h"
 
@@ -21,20 +29,38 @@ using namespace ge;
 
 constexpr int BN_THREADS = 256;
 
+// How the pixel range [0,P) is cut into per-CTA chunks that never straddle the segment boundary: CTAs [0,chunks0)
+// cover segment 0 = [0,P0), CTAs [chunks0,chunks) cover segment 1 = [P0,P).  One segment: P0 = P, chunks0 = chunks.
+struct SegPlan {
+    long long P, P0;
+    int chunks, chunks0;
+    long long ppc0, ppc1;
+    __host__ __device__ __forceinline__ void range(int cta, long long& p0, long long& p1) const {
+        if (cta < chunks0) {
+            p0 = (long long)cta * ppc0;
+            p1 = p0 + ppc0 < P0 ? p0 + ppc0 : P0;
+        } else {
+            p0 = P0 + (long long)(cta - chunks0) * ppc1;
+            p1 = p0 + ppc1 < P ? p0 + ppc1 : P;
+        }
+    }
+    __host__ __device__ __forceinline__ int nseg() const { return P0 < P ? 2 : 1; }
+};
+
 __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) { load8<float>(p, f); }
 
 // ---- stage 1 (forward): per-CTA partial sums of (x - shift) and (x - shift)^2 --------------------
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_partial_stats_kernel(const T* __restrict__ x, const float* __restrict__ shift_src, float* __restrict__ part,
-                        long long P, int C, long long pix_per_cta) {
+                        SegPlan sp, int C) {
     extern __shared__ __align__(16) float sm[];       // [nPL][C] x 2
     const int c8 = C >> 3, nPL = BN_THREADS / c8;
     float* ssum = sm;
     float* ssq = sm + (size_t)nPL * C;
     const int tid = threadIdx.x, co = tid % c8, pl = tid / c8;
-    const long long p0 = (long long)blockIdx.x * pix_per_cta;
-    const long long p1 = min(P, p0 + pix_per_cta);
+    long long p0, p1;
+    sp.range(blockIdx.x, p0, p1);
     float shift[8], a[8], b[8];
     load8f(shift_src + co * 8, shift);
 #pragma unroll
@@ -67,7 +93,8 @@ bn_partial_stats_kernel(const T* __restrict__ x, const float* __restrict__ shift
 
 // Sum the per-CTA partials of 32 channels with FL part-lanes (CTA = 32*FL threads, grid = ceil(C/32)).  The loop is
 // latency-bound (one L2 round trip per row), so every thread keeps 8 independent rows (16 loads) in flight and
-// FL = 32 lanes share the rows: <= 3 trips at 592 partials.
+// FL = 32 lanes share the rows: <= 3 trips at 592 partials.  Every thread of the CTA must call; the result is valid
+// in the threads with lane_p == 0.
 constexpr int FL = 32;
 
 __device__ __forceinline__ void reduce_parts(const float* __restrict__ part, int nparts, int C, int c, int lane_p,
@@ -90,6 +117,7 @@ __device__ __forceinline__ void reduce_parts(const float* __restrict__ part, int
             b += part[(size_t)q * 2 * C + C + c];
         }
     }
+    __syncthreads();                 // a previous call's readers are done with sh
     sh[lane_p][0][threadIdx.x & 31] = a;
     sh[lane_p][1][threadIdx.x & 31] = b;
     __syncthreads();
@@ -100,58 +128,76 @@ __device__ __forceinline__ void reduce_parts(const float* __restrict__ part, int
     }
 }
 
-// ---- stage 2 (forward): batch mean / rstd, running statistics (nn.BatchNorm2d semantics) --------
+// ---- stage 2 (forward): batch mean / rstd per segment, running statistics (nn.BatchNorm2d semantics, one update
+// per segment in segment order), num_batches_tracked += segments ------------------------------------------------
 __global__ void __launch_bounds__(32 * FL)
-bn_finalize_stats_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ shift_src,
+bn_finalize_stats_kernel(const float* __restrict__ part, SegPlan sp, const float* __restrict__ shift_src,
                          float* __restrict__ save_mean, float* __restrict__ save_rstd,
                          float* __restrict__ running_mean, float* __restrict__ running_var,
-                         long long P, int C, float eps, float momentum) {
+                         long long* __restrict__ num_batches_tracked, int C, float eps, float momentum) {
     __shared__ float sh[FL][2][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane8 = threadIdx.x >> 5;
-    float sa, sb;
-    reduce_parts(part, nparts, C, c, lane8, sh, sa, sb);
-    if (lane8 != 0 || c >= C) return;
-    const float inv = 1.f / (float)P;
-    const float md = sa * inv;
-    const float var = fmaxf(sb * inv - md * md, 0.f);          // biased, used to normalise
-    const float mean = md + shift_src[c];
-    save_mean[c] = mean;
-    save_rstd[c] = 1.f / sqrtf(var + eps);
-    if (running_mean != nullptr) {
-        const float unbiased = P > 1 ? var * ((float)P / (float)(P - 1)) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    const bool owner = lane8 == 0 && c < C;
+    const int nseg = sp.nseg();
+    const float shift = c < C ? shift_src[c] : 0.f;          // read before the running mean is updated below
+    float rm = 0.f, rv = 0.f;
+    if (owner && running_mean != nullptr) { rm = running_mean[c]; rv = running_var[c]; }
+    for (int s = 0; s < nseg; ++s) {
+        const int first = s == 0 ? 0 : sp.chunks0, n = s == 0 ? sp.chunks0 : sp.chunks - sp.chunks0;
+        const long long Ps = s == 0 ? sp.P0 : sp.P - sp.P0;
+        float sa, sb;
+        reduce_parts(part + (size_t)first * 2 * C, n, C, c, lane8, sh, sa, sb);
+        if (owner) {
+            const float inv = 1.f / (float)Ps;
+            const float md = sa * inv;
+            const float var = fmaxf(sb * inv - md * md, 0.f);          // biased, used to normalise
+            const float mean = md + shift;
+            save_mean[s * C + c] = mean;
+            save_rstd[s * C + c] = 1.f / sqrtf(var + eps);
+            const float unbiased = Ps > 1 ? var * ((float)Ps / (float)(Ps - 1)) : var;
+            rm = (1.f - momentum) * rm + momentum * mean;
+            rv = (1.f - momentum) * rv + momentum * unbiased;
+        }
     }
+    if (owner && running_mean != nullptr) { running_mean[c] = rm; running_var[c] = rv; }
+    if (num_batches_tracked != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += nseg;
 }
 
 // ---- stage 3 (forward): out = act( x*sc + sh (+ residual) ) --------------------------------------
-// MODE 0: training (sc/sh from save_mean/save_rstd); MODE 1: inference (from running stats, `rstd` = var).
-// A thread owns FOUR channels (one 64-bit bf16 access) of FPIX4 consecutive pixels: the per-channel constants are
-// loaded once and FPIX4 independent loads are in flight before the first use (the first version moved 8 channels per
-// thread at 93 registers -> 21 % occupancy in the round-1 ncu capture).
+// MODE 0: training (sc/sh from save_mean/save_rstd of the pixel's segment); MODE 1: inference (running stats,
+// `rstd` = var).  A thread owns FOUR channels (one 64-bit bf16 access) of FPIX4 consecutive pixels: the per-channel
+// constants are loaded once and FPIX4 independent loads are in flight before the first use.
+// ReLU mask: thread t (this exact mapping is shared with bn_apply_bwd4_kernel and bn_partial_bwd_kernel) writes one
+// uint16 = bit (q*4 + u) set when out[pixel p0+q, channel cc+u] > 0.
 constexpr int FPIX4 = 4;
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 bn_apply_fwd4_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ mean,
                      const float* __restrict__ rstd_or_var, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, T* __restrict__ out, long long P, int C, float eps, int relu) {
+                     const float* __restrict__ beta, T* __restrict__ out, unsigned short* __restrict__ mask,
+                     long long P, long long P0, int C, float eps, int relu) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c4 = C >> 2;
     const int cc = (int)(t % c4) * 4;
     const long long p0 = (t / c4) * FPIX4;
     if (p0 >= P) return;
-    const float4 m4 = *reinterpret_cast<const float4*>(mean + cc), r4 = *reinterpret_cast<const float4*>(rstd_or_var + cc);
     const float4 g4 = *reinterpret_cast<const float4*>(gamma + cc), b4 = *reinterpret_cast<const float4*>(beta + cc);
-    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
     const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
     float sc[4], sh[4];
+    auto constants = [&](int seg) {
+        const float4 m4 = *reinterpret_cast<const float4*>(mean + seg * C + cc);
+        const float4 r4 = *reinterpret_cast<const float4*>(rstd_or_var + seg * C + cc);
+        const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const float rs = (MODE == 0) ? r[u] : 1.f / sqrtf(r[u] + eps);
-        sc[u] = rs * g[u];
-        sh[u] = b[u] - m[u] * sc[u];
-    }
+        for (int u = 0; u < 4; ++u) {
+            const float rs = (MODE == 0) ? r[u] : 1.f / sqrtf(r[u] + eps);
+            sc[u] = rs * g[u];
+            sh[u] = b[u] - m[u] * sc[u];
+        }
+    };
+    int seg = (MODE == 0 && p0 >= P0) ? 1 : 0;
+    constants(seg);
     Vec4<T> v[FPIX4], rv[FPIX4];
 #pragma unroll
     for (int q = 0; q < FPIX4; ++q)
@@ -159,9 +205,11 @@ bn_apply_fwd4_kernel(const T* __restrict__ x, const T* __restrict__ res, const f
             v[q].load(x + (p0 + q) * C + cc);
             if (res != nullptr) rv[q].load(res + (p0 + q) * C + cc);
         }
+    unsigned bits = 0;
 #pragma unroll
     for (int q = 0; q < FPIX4; ++q) {
         if (p0 + q >= P) break;
+        if (MODE == 0 && seg == 0 && p0 + q >= P0) { seg = 1; constants(1); }     // thread straddles the boundary (rare)
         float f[4], rf[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
         v[q].get(f);
         if (res != nullptr) rv[q].get(rf);
@@ -169,29 +217,34 @@ bn_apply_fwd4_kernel(const T* __restrict__ x, const T* __restrict__ res, const f
         for (int u = 0; u < 4; ++u) {
             o[u] = fmaf(f[u], sc[u], sh[u]);
             if (res != nullptr) o[u] += rf[u];
-            if (relu) o[u] = fmaxf(o[u], 0.f);
+            if (relu) {
+                if (o[u] > 0.f) bits |= 1u << (q * 4 + u);
+                o[u] = fmaxf(o[u], 0.f);
+            }
         }
         Vec4<T> w;
         w.set(o);
         w.store(out + (p0 + q) * C + cc);
     }
+    if (mask != nullptr) mask[t] = (unsigned short)bits;
 }
 
 // ---- backward stage 1: partial sums of dyr = dy * relu'(out) and dyr * xhat ----------------------
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_partial_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ out, const T* __restrict__ x,
+bn_partial_bwd_kernel(const T* __restrict__ dy, const unsigned short* __restrict__ mask, const T* __restrict__ x,
                       const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ part,
-                      long long P, int C, long long pix_per_cta, int relu) {
+                      SegPlan sp, int C) {
     extern __shared__ __align__(16) float sm[];
-    const int c8 = C >> 3, nPL = BN_THREADS / c8;
+    const int c8 = C >> 3, nPL = BN_THREADS / c8, c4 = C >> 2;
     float* s1 = sm;
     float* s2 = sm + (size_t)nPL * C;
     const int tid = threadIdx.x, co = tid % c8, pl = tid / c8, cc = co * 8;
-    const long long p0 = (long long)blockIdx.x * pix_per_cta;
-    const long long p1 = min(P, p0 + pix_per_cta);
+    long long p0, p1;
+    sp.range(blockIdx.x, p0, p1);
+    const int seg = blockIdx.x < sp.chunks0 ? 0 : 1;
     float m[8], r[8], a[8], b[8];
-    load8f(mean + cc, m); load8f(rstd + cc, r);
+    load8f(mean + seg * C + cc, m); load8f(rstd + seg * C + cc, r);
 #pragma unroll
     for (int u = 0; u < 8; ++u) { a[u] = 0.f; b[u] = 0.f; }
     if (pl < nPL) {
@@ -200,11 +253,16 @@ bn_partial_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ out, const
             float g[8], xv[8];
             load8<T>(dy + p * C + cc, g);
             load8<T>(x + p * C + cc, xv);
-            if (relu) {
-                float ov[8];
-                load8<T>(out + p * C + cc, ov);
+            if (mask != nullptr) {
+                // the two uint16 words of the apply threads that own channels cc..cc+3 and cc+4..cc+7 of pixel p
+                const unsigned w = *reinterpret_cast<const unsigned*>(mask + (p >> 2) * c4 + (cc >> 2));
+                const unsigned sft = (unsigned)(p & 3) * 4;
+                const unsigned lo = (w >> sft) & 0xFu, hi = (w >> (16 + sft)) & 0xFu;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) g[u] = (ov[u] > 0.f) ? g[u] : 0.f;
+                for (int u = 0; u < 4; ++u) {
+                    g[u] = (lo >> u) & 1u ? g[u] : 0.f;
+                    g[4 + u] = (hi >> u) & 1u ? g[4 + u] : 0.f;
+                }
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -225,66 +283,84 @@ bn_partial_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ out, const
     }
 }
 
-// ---- backward stage 2: dbeta = S1, dgamma = S2 ----------------------------------------------------
+// ---- backward stage 2: per segment S1 = sum dyr, S2 = sum dyr*xhat -> seg_sums [2][nseg][C]; dbeta = sum_s S1,
+// dgamma = sum_s S2 ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * FL)
-bn_finalize_bwd_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, int C) {
+bn_finalize_bwd_kernel(const float* __restrict__ part, SegPlan sp, float* __restrict__ seg_sums,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
     __shared__ float sh[FL][2][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane8 = threadIdx.x >> 5;
-    float sa, sb;
-    reduce_parts(part, nparts, C, c, lane8, sh, sa, sb);
-    if (lane8 != 0 || c >= C) return;
-    dbeta[c] = sa;
-    dgamma[c] = sb;
+    const bool owner = lane8 == 0 && c < C;
+    const int nseg = sp.nseg();
+    float ta = 0.f, tb = 0.f;
+    for (int s = 0; s < nseg; ++s) {
+        const int first = s == 0 ? 0 : sp.chunks0, n = s == 0 ? sp.chunks0 : sp.chunks - sp.chunks0;
+        float sa, sb;
+        reduce_parts(part + (size_t)first * 2 * C, n, C, c, lane8, sh, sa, sb);
+        if (owner) {
+            seg_sums[s * C + c] = sa;
+            seg_sums[(nseg + s) * C + c] = sb;
+            ta += sa; tb += sb;
+        }
+    }
+    if (owner) { dbeta[c] = ta; dgamma[c] = tb; }
 }
 
-// ---- backward stage 3: dx = rstd*gamma*(dyr - S1/P - xhat*S2/P);  dres = dyr ------------------------
-// FOUR channels per thread (one 64-bit bf16 access) of BPIX4 consecutive pixels -- about half the live state of the
-// first, 8-channel version (111 registers, 20 % occupancy, 44 % of DRAM peak in the round-1 ncu capture), so twice
-// as many loads are in flight per SM.
+// ---- backward stage 3: dx = rstd*gamma*(dyr - S1/P - xhat*S2/P) with the segment's S1, S2, P;  dres = dyr -------
+// FOUR channels per thread (one 64-bit bf16 access) of BPIX4 consecutive pixels; same thread <-> element mapping as
+// bn_apply_fwd4_kernel (the ReLU mask word of thread t is mask[t]).
 constexpr int BPIX4 = 4;
+static_assert(BPIX4 == FPIX4, "the ReLU mask layout is shared by the forward and backward apply kernels");
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_apply_bwd4_kernel(const T* __restrict__ dy, const T* __restrict__ out, const T* __restrict__ x,
+bn_apply_bwd4_kernel(const T* __restrict__ dy, const unsigned short* __restrict__ mask, const T* __restrict__ x,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                     const float* __restrict__ gamma, const float* __restrict__ dgamma,
-                     const float* __restrict__ dbeta, T* __restrict__ dx, T* __restrict__ dres,
-                     long long P, int C, float invP, int relu) {
+                     const float* __restrict__ gamma, const float* __restrict__ seg_sums,
+                     T* __restrict__ dx, T* __restrict__ dres, long long P, long long P0, int C) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c4 = C >> 2;
     const int cc = (int)(t % c4) * 4;
     const long long p0 = (t / c4) * BPIX4;
     if (p0 >= P) return;
-    const float4 m4 = *reinterpret_cast<const float4*>(mean + cc), r4 = *reinterpret_cast<const float4*>(rstd + cc);
+    const int nseg = P0 < P ? 2 : 1;
     const float4 g4 = *reinterpret_cast<const float4*>(gamma + cc);
-    const float4 b4 = *reinterpret_cast<const float4*>(dbeta + cc), q4 = *reinterpret_cast<const float4*>(dgamma + cc);
-    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
-    const float s1[4] = {b4.x, b4.y, b4.z, b4.w}, s2[4] = {q4.x, q4.y, q4.z, q4.w};
-    float k0[4], k1[4], k2[4];
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    float m[4], k0[4], k1[4], k2[4];
+    auto constants = [&](int seg) {          // dx = k0*dyr - k1 - (x-m)*k2
+        const float4 m4 = *reinterpret_cast<const float4*>(mean + seg * C + cc);
+        const float4 r4 = *reinterpret_cast<const float4*>(rstd + seg * C + cc);
+        const float4 b4 = *reinterpret_cast<const float4*>(seg_sums + seg * C + cc);
+        const float4 q4 = *reinterpret_cast<const float4*>(seg_sums + (nseg + seg) * C + cc);
+        const float r[4] = {r4.x, r4.y, r4.z, r4.w}, s1[4] = {b4.x, b4.y, b4.z, b4.w}, s2[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float invP = 1.f / (float)(seg == 0 ? P0 : P - P0);
+        m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {            // dx = k0*dyr - k1 - (x-m)*k2
-        k0[u] = r[u] * g[u];
-        k1[u] = k0[u] * s1[u] * invP;
-        k2[u] = k0[u] * s2[u] * invP * r[u];
-    }
-    Vec4<T> gv[BPIX4], xv[BPIX4], ov[BPIX4];
+        for (int u = 0; u < 4; ++u) {
+            k0[u] = r[u] * g[u];
+            k1[u] = k0[u] * s1[u] * invP;
+            k2[u] = k0[u] * s2[u] * invP * r[u];
+        }
+    };
+    int seg = p0 >= P0 ? 1 : 0;
+    constants(seg);
+    Vec4<T> gv[BPIX4], xv[BPIX4];
 #pragma unroll
     for (int q = 0; q < BPIX4; ++q)
         if (p0 + q < P) {
             gv[q].load(dy + (p0 + q) * C + cc);
             xv[q].load(x + (p0 + q) * C + cc);
-            if (relu) ov[q].load(out + (p0 + q) * C + cc);
         }
+    const unsigned bits = mask != nullptr ? (unsigned)mask[t] : 0xFFFFu;
 #pragma unroll
     for (int q = 0; q < BPIX4; ++q) {
         if (p0 + q >= P) break;
-        float gf[4], xf[4], of[4] = {1.f, 1.f, 1.f, 1.f}, o[4];
+        if (seg == 0 && p0 + q >= P0) { seg = 1; constants(1); }
+        float gf[4], xf[4], o[4];
         gv[q].get(gf); xv[q].get(xf);
-        if (relu) ov[q].get(of);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float gq = (relu && !(of[u] > 0.f)) ? 0.f : gf[u];
+            const float gq = (bits >> (q * 4 + u)) & 1u ? gf[u] : 0.f;
             gf[u] = gq;
             o[u] = k0[u] * gq - k1[u] - (xf[u] - m[u]) * k2[u];
         }
@@ -300,8 +376,28 @@ int bn_chunks(long long P, int C) {
     long long want = P / ((long long)nPL * 8);           // >= 8 pixels per pixel-lane
     const long long cap = (long long)ge::sm_count() * 4;
     if (want > cap) want = cap;
-    if (want < 1) want = 1;
+    if (want < 2) want = 2;                              // room for one chunk per segment
     return (int)want;
+}
+
+SegPlan bn_plan(long long P, long long P_split, int C) {
+    SegPlan sp;
+    sp.P = P;
+    sp.P0 = (P_split > 0 && P_split < P) ? P_split : P;
+    sp.chunks = bn_chunks(P, C);
+    if (sp.P0 < P) {
+        long long c0 = (sp.chunks * sp.P0 + P / 2) / P;
+        if (c0 < 1) c0 = 1;
+        if (c0 > sp.chunks - 1) c0 = sp.chunks - 1;
+        sp.chunks0 = (int)c0;
+        sp.ppc0 = ge::cdivll(sp.P0, sp.chunks0);
+        sp.ppc1 = ge::cdivll(P - sp.P0, sp.chunks - sp.chunks0);
+    } else {
+        sp.chunks0 = sp.chunks;
+        sp.ppc0 = ge::cdivll(P, sp.chunks);
+        sp.ppc1 = 1;
+    }
+    return sp;
 }
 
 bool bn_shape_ok(int C) { return C % 8 == 0 && C / 8 <= BN_THREADS && BN_THREADS % (C / 8) == 0; }
@@ -310,48 +406,57 @@ size_t bn_smem(int C) { return (size_t)2 * (BN_THREADS / (C / 8)) * C * sizeof(f
 
 }  // namespace
 
+// partials [chunks][2][C] followed by the backward's per-segment sums [2][2][C]
 extern "C" size_t ge_bn_workspace_bytes(long long P, int C) {
     if (P <= 0 || C <= 0 || !bn_shape_ok(C)) return 0;
-    return (size_t)bn_chunks(P, C) * 2 * C * sizeof(float);
+    return ((size_t)bn_chunks(P, C) * 2 * C + 4 * (size_t)C) * sizeof(float);
 }
 
-// x, residual (or NULL), out: [P,C] NHWC-flattened (P = N*H*W) in `dtype`; gamma, beta, running_*,
-// save_mean, save_rstd: fp32 [C].  running_* may be NULL (track_running_stats=False).
+extern "C" size_t ge_bn_relu_mask_bytes(long long P, int C) {
+    if (P <= 0 || C <= 0 || C % 8 != 0) return 0;
+    return (size_t)ge::cdivll(P, FPIX4) * (C / 4) * sizeof(unsigned short);
+}
+
+// x, residual (or NULL), out: [P,C] NHWC-flattened (P = N*H*W) in `dtype`; gamma, beta, running_* fp32 [C];
+// save_mean, save_rstd fp32 [nseg][C] with nseg = 2 when 0 < P_split < P, else 1.  running_* may be NULL
+// (track_running_stats=False); num_batches_tracked (int64, or NULL) is incremented by nseg on the device;
+// relu_mask (ge_bn_relu_mask_bytes, or NULL) receives the 1-bit ReLU mask the backward consumes.
 extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float* gamma, const float* beta,
-                               float* running_mean, float* running_var, float momentum, float eps,
-                               void* out, float* save_mean, float* save_rstd, void* workspace, size_t workspace_bytes,
-                               int dtype, long long P, int C, int relu, ge_stream_t stream) {
+                               float* running_mean, float* running_var, long long* num_batches_tracked,
+                               float momentum, float eps, void* out, float* save_mean, float* save_rstd,
+                               void* relu_mask, void* workspace, size_t workspace_bytes,
+                               int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream) {
     GE_REQUIRE(x && gamma && beta && out && save_mean && save_rstd && workspace, GE_ERR_ARG, "ge_bn_fwd_train: null pointer");
-    GE_REQUIRE(P > 0 && C > 0, GE_ERR_ARG, "ge_bn_fwd_train: bad dimension");
+    GE_REQUIRE(P > 0 && C > 0 && P_split >= 0 && P_split <= P, GE_ERR_ARG, "ge_bn_fwd_train: bad dimension");
     GE_REQUIRE(bn_shape_ok(C), GE_ERR_SHAPE, "ge_bn_fwd_train: unsupported channel count C=%d (C%%8==0, C/8 | 256)", C);
     GE_REQUIRE(workspace_bytes >= ge_bn_workspace_bytes(P, C), GE_ERR_ARG, "ge_bn_fwd_train: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const int chunks = bn_chunks(P, C);
-    const long long ppc = ge::cdivll(P, chunks);
+    const SegPlan sp = bn_plan(P, P_split, C);
     const size_t smem = bn_smem(C);
     float* part = static_cast<float*>(workspace);
-    // shift = running mean when tracked (close to the batch mean), else beta-free zero shift via gamma-less trick
+    // shift = running mean when tracked (close to the batch mean), else a zero shift
     const float* shift = running_mean != nullptr ? running_mean : save_mean;
     if (running_mean == nullptr) GE_CUDA(cudaMemsetAsync(save_mean, 0, (size_t)C * sizeof(float), st), "ge_bn_fwd_train(memset)");
     static size_t c0 = 0, c1 = 0;
     if (dtype == GE_DTYPE_F32) {
         if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(bn_partial_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_fwd_train(attr)"); c0 = smem; }
-        bn_partial_stats_kernel<float><<<chunks, BN_THREADS, smem, st>>>((const float*)x, shift, part, P, C, ppc);
+        bn_partial_stats_kernel<float><<<sp.chunks, BN_THREADS, smem, st>>>((const float*)x, shift, part, sp, C);
     } else if (dtype == GE_DTYPE_BF16) {
         if (smem > c1) { GE_CUDA(cudaFuncSetAttribute(bn_partial_stats_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_fwd_train(attr)"); c1 = smem; }
-        bn_partial_stats_kernel<bf16><<<chunks, BN_THREADS, smem, st>>>((const bf16*)x, shift, part, P, C, ppc);
+        bn_partial_stats_kernel<bf16><<<sp.chunks, BN_THREADS, smem, st>>>((const bf16*)x, shift, part, sp, C);
     } else { ge_set_error("ge_bn_fwd_train: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_bn_fwd_train(stats)");
-    bn_finalize_stats_kernel<<<ge::cdiv(C, 32), 32 * FL, 0, st>>>(part, chunks, shift, save_mean, save_rstd,
-                                                               running_mean, running_var, P, C, eps, momentum);
+    bn_finalize_stats_kernel<<<ge::cdiv(C, 32), 32 * FL, 0, st>>>(part, sp, shift, save_mean, save_rstd,
+                                                               running_mean, running_var, num_batches_tracked, C, eps, momentum);
     GE_CHECK_LAUNCH("ge_bn_fwd_train(finalize)");
     const unsigned blocks4 = (unsigned)ge::cdivll(ge::cdivll(P, FPIX4) * (C / 4), 256);
+    unsigned short* mk = relu ? static_cast<unsigned short*>(relu_mask) : nullptr;
     if (dtype == GE_DTYPE_F32)
         bn_apply_fwd4_kernel<float, 0><<<blocks4, 256, 0, st>>>((const float*)x, (const float*)residual, save_mean, save_rstd,
-                                                                 gamma, beta, (float*)out, P, C, eps, relu);
+                                                                 gamma, beta, (float*)out, mk, P, sp.P0, C, eps, relu);
     else
         bn_apply_fwd4_kernel<bf16, 0><<<blocks4, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, save_mean, save_rstd,
-                                                                gamma, beta, (bf16*)out, P, C, eps, relu);
+                                                                gamma, beta, (bf16*)out, mk, P, sp.P0, C, eps, relu);
     GE_CHECK_LAUNCH("ge_bn_fwd_train(apply)");
     return GE_OK;
 }
@@ -366,57 +471,57 @@ extern "C" int ge_bn_fwd_eval(const void* x, const void* residual, const float* 
     const unsigned blocks4 = (unsigned)ge::cdivll(ge::cdivll(P, FPIX4) * (C / 4), 256);
     if (dtype == GE_DTYPE_F32)
         bn_apply_fwd4_kernel<float, 1><<<blocks4, 256, 0, st>>>((const float*)x, (const float*)residual, running_mean, running_var,
-                                                                 gamma, beta, (float*)out, P, C, eps, relu);
+                                                                 gamma, beta, (float*)out, nullptr, P, P, C, eps, relu);
     else if (dtype == GE_DTYPE_BF16)
         bn_apply_fwd4_kernel<bf16, 1><<<blocks4, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, running_mean, running_var,
-                                                                gamma, beta, (bf16*)out, P, C, eps, relu);
+                                                                gamma, beta, (bf16*)out, nullptr, P, P, C, eps, relu);
     else { ge_set_error("ge_bn_fwd_eval: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_bn_fwd_eval");
     return GE_OK;
 }
 
-// Training-mode backward: mean / rstd = save_mean / save_rstd of the forward.  dres (or NULL) receives the
-// gradient of the residual input.  dgamma, dbeta fp32 [C] (overwritten).
-extern "C" int ge_bn_bwd(const void* dy, const void* out, const void* x, const float* gamma,
-                         const float* mean, const float* rstd_or_var, float eps, void* dx, void* dres,
+// Training-mode backward: mean / rstd = save_mean / save_rstd of the forward ([nseg][C]); relu_mask = the forward's
+// mask (required when relu != 0).  dres (or NULL) receives the gradient of the residual input.  dgamma, dbeta fp32 [C]
+// (overwritten).
+extern "C" int ge_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float* gamma,
+                         const float* mean, const float* rstd, void* dx, void* dres,
                          float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-                         int dtype, long long P, int C, int relu, ge_stream_t stream) {
-    GE_REQUIRE(dy && x && gamma && mean && rstd_or_var && dx && dgamma && dbeta && workspace, GE_ERR_ARG, "ge_bn_bwd: null pointer");
-    GE_REQUIRE(!relu || out, GE_ERR_ARG, "ge_bn_bwd: the forward output is needed for the ReLU mask");
-    GE_REQUIRE(P > 0 && C > 0, GE_ERR_ARG, "ge_bn_bwd: bad dimension");
+                         int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream) {
+    GE_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, GE_ERR_ARG, "ge_bn_bwd: null pointer");
+    GE_REQUIRE(!relu || relu_mask, GE_ERR_ARG, "ge_bn_bwd: the forward's ReLU mask is needed");
+    GE_REQUIRE(P > 0 && C > 0 && P_split >= 0 && P_split <= P, GE_ERR_ARG, "ge_bn_bwd: bad dimension");
     GE_REQUIRE(bn_shape_ok(C), GE_ERR_SHAPE, "ge_bn_bwd: unsupported channel count C=%d", C);
     GE_REQUIRE(workspace_bytes >= ge_bn_workspace_bytes(P, C), GE_ERR_ARG, "ge_bn_bwd: workspace too small");
     GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_bwd: unsupported dtype %d", dtype);
     cudaStream_t st = (cudaStream_t)stream;
-    const int chunks = bn_chunks(P, C);
-    const long long ppc = ge::cdivll(P, chunks);
+    const SegPlan sp = bn_plan(P, P_split, C);
     const size_t smem = bn_smem(C);
     float* part = static_cast<float*>(workspace);
+    float* seg_sums = part + (size_t)sp.chunks * 2 * C;
+    const unsigned short* mk = relu ? static_cast<const unsigned short*>(relu_mask) : nullptr;
     static size_t c0 = 0, c1 = 0;
-    const float* rstd = rstd_or_var;
     if (dtype == GE_DTYPE_F32) {
         if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(bn_partial_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_bwd(attr)"); c0 = smem; }
     } else {
         if (smem > c1) { GE_CUDA(cudaFuncSetAttribute(bn_partial_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_bwd(attr)"); c1 = smem; }
     }
     if (dtype == GE_DTYPE_F32)
-        bn_partial_bwd_kernel<float><<<chunks, BN_THREADS, smem, st>>>((const float*)dy, (const float*)out, (const float*)x,
-                                                                       mean, rstd, part, P, C, ppc, relu);
+        bn_partial_bwd_kernel<float><<<sp.chunks, BN_THREADS, smem, st>>>((const float*)dy, mk, (const float*)x,
+                                                                          mean, rstd, part, sp, C);
     else
-        bn_partial_bwd_kernel<bf16><<<chunks, BN_THREADS, smem, st>>>((const bf16*)dy, (const bf16*)out, (const bf16*)x,
-                                                                      mean, rstd, part, P, C, ppc, relu);
+        bn_partial_bwd_kernel<bf16><<<sp.chunks, BN_THREADS, smem, st>>>((const bf16*)dy, mk, (const bf16*)x,
+                                                                         mean, rstd, part, sp, C);
     GE_CHECK_LAUNCH("ge_bn_bwd(partial)");
-    bn_finalize_bwd_kernel<<<ge::cdiv(C, 32), 32 * FL, 0, st>>>(part, chunks, dgamma, dbeta, C);
+    bn_finalize_bwd_kernel<<<ge::cdiv(C, 32), 32 * FL, 0, st>>>(part, sp, seg_sums, dgamma, dbeta, C);
     GE_CHECK_LAUNCH("ge_bn_bwd(finalize)");
-    const float invP = 1.f / (float)P;
     const long long total4 = ge::cdivll(P, BPIX4) * (C / 4);
     const unsigned blocks4 = (unsigned)ge::cdivll(total4, 256);
     if (dtype == GE_DTYPE_F32)
-        bn_apply_bwd4_kernel<float><<<blocks4, 256, 0, st>>>((const float*)dy, (const float*)out, (const float*)x, mean, rstd,
-            gamma, dgamma, dbeta, (float*)dx, (float*)dres, P, C, invP, relu);
+        bn_apply_bwd4_kernel<float><<<blocks4, 256, 0, st>>>((const float*)dy, mk, (const float*)x, mean, rstd,
+            gamma, seg_sums, (float*)dx, (float*)dres, P, sp.P0, C);
     else
-        bn_apply_bwd4_kernel<bf16><<<blocks4, 256, 0, st>>>((const bf16*)dy, (const bf16*)out, (const bf16*)x, mean, rstd,
-            gamma, dgamma, dbeta, (bf16*)dx, (bf16*)dres, P, C, invP, relu);
+        bn_apply_bwd4_kernel<bf16><<<blocks4, 256, 0, st>>>((const bf16*)dy, mk, (const bf16*)x, mean, rstd,
+            gamma, seg_sums, (bf16*)dx, (bf16*)dres, P, sp.P0, C);
     GE_CHECK_LAUNCH("ge_bn_bwd(apply)");
     return GE_OK;
 }

@@ -18,20 +18,23 @@ constexpr int SD_THREADS = 256;
 constexpr int SD_WARPS = SD_THREADS / 32;
 constexpr int DC = 32;  // feature chunk staged through shared memory for the cost matrix
 
-__host__ __device__ inline size_t sd_fwd_smem_floats(int P1, int P2) {
-    return (size_t)P1 * P2 + P1 + P2 + (size_t)(P1 + P2) * (DC + 1) + 32;
+// `spill`: the P1 x P2 matrices do not fit one CTA's shared memory (node sets of ~250-320 rows, config 3): C lives in
+// its global output array and the backward's dC accumulator in its global output array instead (both are L2-resident:
+// <= 0.5 MB), everything else is unchanged.
+__host__ __device__ inline size_t sd_fwd_smem_floats(int P1, int P2, bool spill) {
+    return (spill ? 0 : (size_t)P1 * P2) + P1 + P2 + (size_t)(P1 + P2) * (DC + 1) + 32;
 }
-__host__ __device__ inline size_t sd_bwd_smem_floats(int P1, int P2) {
-    return (size_t)2 * P1 * P2 + 4 * (size_t)(P1 + P2) + 2 * (size_t)(P1 > P2 ? P1 : P2) + 32;
+__host__ __device__ inline size_t sd_bwd_smem_floats(int P1, int P2, bool spill) {
+    return (spill ? 0 : (size_t)2 * P1 * P2) + 4 * (size_t)(P1 + P2) + 2 * (size_t)(P1 > P2 ? P1 : P2) + 32;
 }
 
 __global__ void __launch_bounds__(SD_THREADS)
 sd_iterate_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ Cout,
                   float* __restrict__ hist_u, float* __restrict__ hist_v, float* __restrict__ err,
-                  int P1, int P2, int D, float eps, int max_iter) {
+                  int P1, int P2, int D, float eps, int max_iter, int spill) {
     extern __shared__ __align__(16) float smem[];
-    float* C = smem;                       // [P1][P2]
-    float* u = C + (size_t)P1 * P2;        // [P1]
+    float* C = spill ? Cout + (size_t)blockIdx.x * P1 * P2 : smem;       // [P1][P2]
+    float* u = spill ? smem : smem + (size_t)P1 * P2;                    // [P1]
     float* v = u + P1;                     // [P2]
     float* xs = v + P2;                    // [P1][DC+1]
     float* ys = xs + (size_t)P1 * (DC + 1);// [P2][DC+1]
@@ -74,7 +77,8 @@ sd_iterate_kernel(const float* __restrict__ x, const float* __restrict__ y, floa
         }
     }
     __syncthreads();
-    for (int p = tid; p < npairs; p += SD_THREADS) Cout[p] = C[p];
+    if (!spill)
+        for (int p = tid; p < npairs; p += SD_THREADS) Cout[p] = C[p];
     for (int i = tid; i < P1; i += SD_THREADS) u[i] = 0.f;
     for (int j = tid; j < P2; j += SD_THREADS) v[j] = 0.f;
     __syncthreads();
@@ -167,12 +171,12 @@ __global__ void __launch_bounds__(SD_THREADS)
 sd_bwd_kernel(const float* __restrict__ Cg, const float* __restrict__ hist_u,
               const float* __restrict__ hist_v, const int* __restrict__ nits,
               const float* __restrict__ gcost, float* __restrict__ dC,
-              int P1, int P2, float eps, int max_iter) {
+              int P1, int P2, float eps, int max_iter, int spill) {
     extern __shared__ __align__(16) float smem[];
     const int PM = P1 > P2 ? P1 : P2;
-    float* C = smem;                        // [P1][P2]
-    float* E = C + (size_t)P1 * P2;         // [P1][P2]  dC accumulator
-    float* ut = E + (size_t)P1 * P2;        // [P1] u_t
+    const float* C = spill ? Cg + (size_t)blockIdx.x * P1 * P2 : smem;             // [P1][P2]
+    float* E = spill ? dC + (size_t)blockIdx.x * P1 * P2 : smem + (size_t)P1 * P2;  // [P1][P2]  dC accumulator
+    float* ut = spill ? smem : smem + (size_t)2 * P1 * P2;                          // [P1] u_t
     float* up = ut + P1;                    // [P1] u_{t-1}
     float* vt = up + P1;                    // [P2] v_t
     float* vp = vt + P2;                    // [P2] v_{t-1}
@@ -191,7 +195,8 @@ sd_bwd_kernel(const float* __restrict__ Cg, const float* __restrict__ hist_u,
     hist_v += (size_t)b * max_iter * P2;
     const float inv_eps = 1.f / eps;
 
-    for (int p = tid; p < P1 * P2; p += SD_THREADS) C[p] = Cg[p];
+    if (!spill)
+        for (int p = tid; p < P1 * P2; p += SD_THREADS) smem[p] = Cg[p];
     for (int i = tid; i < P1; i += SD_THREADS) ut[i] = (n > 0) ? hist_u[(size_t)(n - 1) * P1 + i] : 0.f;
     for (int j = tid; j < P2; j += SD_THREADS) vt[j] = (n > 0) ? hist_v[(size_t)(n - 1) * P2 + j] : 0.f;
     __syncthreads();
@@ -270,21 +275,26 @@ sd_bwd_kernel(const float* __restrict__ Cg, const float* __restrict__ hist_u,
         for (int j = tid; j < P2; j += SD_THREADS) vt[j] = vp[j];
         __syncthreads();
     }
-    for (int p = tid; p < P1 * P2; p += SD_THREADS) dC[p] = E[p];
+    if (!spill)
+        for (int p = tid; p < P1 * P2; p += SD_THREADS) dC[p] = E[p];
 }
 
 // dx_id = 2*sum_j dC_ij (x_id - y_jd),  dy_jd = -2*sum_i dC_ij (x_id - y_jd)
 __global__ void __launch_bounds__(256)
 sd_bwd_xy_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dC,
-                 float* __restrict__ dx, float* __restrict__ dy, int P1, int P2, int D) {
-    extern __shared__ __align__(16) float g[];  // [P1][P2]
+                 float* __restrict__ dx, float* __restrict__ dy, int P1, int P2, int D, int spill) {
+    extern __shared__ __align__(16) float gs[];  // [P1][P2]
     const int b = blockIdx.y;
     x += (size_t)b * P1 * D;
     y += (size_t)b * P2 * D;
     dC += (size_t)b * P1 * P2;
     dx += (size_t)b * P1 * D;
     dy += (size_t)b * P2 * D;
-    for (int p = threadIdx.x; p < P1 * P2; p += blockDim.x) g[p] = dC[p];
+    const float* g = dC;
+    if (!spill) {
+        for (int p = threadIdx.x; p < P1 * P2; p += blockDim.x) gs[p] = dC[p];
+        g = gs;
+    }
     __syncthreads();
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
@@ -314,12 +324,13 @@ extern "C" int ge_sinkhorn_distance_fwd(const float* x, const float* y, float* C
                "ge_sinkhorn_distance_fwd: null pointer");
     GE_REQUIRE(B > 0 && P1 > 0 && P2 > 0 && D > 0 && max_iter >= 0 && eps > 0.f, GE_ERR_ARG,
                "ge_sinkhorn_distance_fwd: bad dimension");
-    const size_t smem = sd_fwd_smem_floats(P1, P2) * sizeof(float);
+    const int spill = sd_fwd_smem_floats(P1, P2, false) * sizeof(float) > kCap;
+    const size_t smem = sd_fwd_smem_floats(P1, P2, spill) * sizeof(float);
     GE_REQUIRE(smem <= kCap, GE_ERR_CAPACITY,
-               "ge_sinkhorn_distance_fwd: P1=%d x P2=%d does not fit one CTA's shared memory", P1, P2);
+               "ge_sinkhorn_distance_fwd: P1=%d + P2=%d rows do not fit one CTA's shared memory", P1, P2);
     cudaStream_t st = (cudaStream_t)stream;
     { static size_t ge_max_smem__ = 0; if ((size_t)(smem) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(sd_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)), "ge_sinkhorn_distance_fwd(attr)"); ge_max_smem__ = (size_t)(smem); } }
-    sd_iterate_kernel<<<B, SD_THREADS, smem, st>>>(x, y, C, hist_u, hist_v, err, P1, P2, D, eps, max_iter);
+    sd_iterate_kernel<<<B, SD_THREADS, smem, st>>>(x, y, C, hist_u, hist_v, err, P1, P2, D, eps, max_iter, spill);
     GE_CHECK_LAUNCH("ge_sinkhorn_distance_fwd(iterate)");
     sd_finalize_kernel<<<B, SD_THREADS, 0, st>>>(C, hist_u, hist_v, err, pi, cost, nits, B, P1, P2, eps, max_iter, thresh);
     GE_CHECK_LAUNCH("ge_sinkhorn_distance_fwd(finalize)");
@@ -335,17 +346,19 @@ extern "C" int ge_sinkhorn_distance_bwd(const float* x, const float* y, const fl
                "ge_sinkhorn_distance_bwd: null pointer");
     GE_REQUIRE(B > 0 && P1 > 0 && P2 > 0 && D > 0 && max_iter >= 0 && eps > 0.f, GE_ERR_ARG,
                "ge_sinkhorn_distance_bwd: bad dimension");
-    const size_t smem = sd_bwd_smem_floats(P1, P2) * sizeof(float);
+    const int spill = sd_bwd_smem_floats(P1, P2, false) * sizeof(float) > kCap;
+    const size_t smem = sd_bwd_smem_floats(P1, P2, spill) * sizeof(float);
     GE_REQUIRE(smem <= kCap, GE_ERR_CAPACITY,
-               "ge_sinkhorn_distance_bwd: P1=%d x P2=%d does not fit one CTA's shared memory", P1, P2);
+               "ge_sinkhorn_distance_bwd: P1=%d + P2=%d rows do not fit one CTA's shared memory", P1, P2);
     cudaStream_t st = (cudaStream_t)stream;
     { static size_t ge_max_smem__ = 0; if ((size_t)(smem) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(sd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)), "ge_sinkhorn_distance_bwd(attr)"); ge_max_smem__ = (size_t)(smem); } }
-    sd_bwd_kernel<<<B, SD_THREADS, smem, st>>>(C, hist_u, hist_v, nits, gcost, dC, P1, P2, eps, max_iter);
+    sd_bwd_kernel<<<B, SD_THREADS, smem, st>>>(C, hist_u, hist_v, nits, gcost, dC, P1, P2, eps, max_iter, spill);
     GE_CHECK_LAUNCH("ge_sinkhorn_distance_bwd(sweep)");
-    const size_t smem2 = (size_t)P1 * P2 * sizeof(float);
+    const int spill2 = (size_t)P1 * P2 * sizeof(float) > kCap;
+    const size_t smem2 = spill2 ? 0 : (size_t)P1 * P2 * sizeof(float);
     { static size_t ge_max_smem__ = 0; if ((size_t)(smem2) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(sd_bwd_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem2)), "ge_sinkhorn_distance_bwd(attr2)"); ge_max_smem__ = (size_t)(smem2); } }
     dim3 grid(ge::cdiv(D, 256), B);
-    sd_bwd_xy_kernel<<<grid, 256, smem2, st>>>(x, y, dC, dx, dy, P1, P2, D);
+    sd_bwd_xy_kernel<<<grid, 256, smem2, st>>>(x, y, dC, dx, dy, P1, P2, D, spill2);
     GE_CHECK_LAUNCH("ge_sinkhorn_distance_bwd(xy)");
     return GE_OK;
 }

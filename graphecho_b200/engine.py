@@ -28,7 +28,21 @@ from .models.TGCN import TGCN
 from .models.vig import Grapher
 from .utils.losses import DiceLoss
 from .utils.sinkhorn_distance import SinkhornDistance
+from . import functional as GF
 from . import synth
+
+
+def preset(config: int, **over) -> "EngineConfig":
+    """The workloads BASELINE.json's `configs` name.
+    2: EchoNet-shape 112x112 clips, FPN(resnet, nc=2) + ViG Grapher(p2) + GModule + 4 discriminators  (also config 5)
+    3: CAMUS-shape 256x256 frames, FPN(resnet, nc=4) + GModule + 4 discriminators + SinkhornDistance on the node sets
+    4: CardiacUDA-shape 256x256, FPN(VGG16, nc=3) + GModule + 4 discriminators + TGCN temporal module on 8-frame clips"""
+    base = {2: dict(backbone="resnet", hw=112, num_classes=2, vig_grapher=True),
+            5: dict(backbone="resnet", hw=112, num_classes=2, vig_grapher=True),
+            3: dict(backbone="resnet", hw=256, num_classes=4, vig_grapher=False, sinkhorn_nodes=True),
+            4: dict(backbone="VGG16", hw=256, num_classes=3, vig_grapher=False, temporal_graph=True, clip_frames=8)}[config]
+    base.update(over)
+    return EngineConfig(**base)
 
 
 @dataclass
@@ -40,8 +54,12 @@ class EngineConfig:
     graph_matching: bool = True
     discriminator: bool = True
     vig_grapher: bool = True            # Grapher(256, k=9, 'mr', 'gelu', 'batch') on p2 (config 2)
-    temporal_graph: bool = False        # TGCN on [b,t] clips (256x256 only, Appendix A-2)
+    temporal_graph: bool = False        # TGCN on [b,t] clips (256x256 only, Appendix A-2): the step takes a `temporal`
+                                        # input (clips + source-clip masks) beside the single-frame streams
     clip_frames: int = 8
+    sinkhorn_nodes: bool = False        # config 3: SinkhornDistance(0.1, 5, 'mean') between the matched node sets
+    sinkhorn_weight: float = 0.001
+    per_domain_bn: bool = True          # BatchNorm statistics per domain, as the reference's two network calls per step
     sync_bn: bool = True
     seg_weight: float = 1.0             # train_camus_echo.py:212 uses 0.05
     lr_net: float = 3e-4
@@ -219,8 +237,10 @@ class UDAEngine:
         self.network = self.network.to(memory_format=torch.channels_last)
         if world_size > 1 and cfg.sync_bn:
             self.network = nn.SyncBatchNorm.convert_sync_batchnorm(self.network)
-        self._trunk, self._head = _Trunk(self.network), _Head(self.network)
+        self._trunk_raw, self._head_raw = _Trunk(self.network), _Head(self.network)
+        self._trunk, self._head = self._trunk_raw, self._head_raw
         self.aux: dict[str, nn.Module] = {}
+        self._gmodule = None
         if cfg.graph_matching:
             gm = GModule(in_channels=256, num_classes=nc, device=device).to(device)
             gm.cluster_backend = cfg.cluster_backend
@@ -236,7 +256,7 @@ class UDAEngine:
                                           (cfg.hw // 4) ** 2, 0.0, False).to(device)
         if cfg.temporal_graph:
             self.aux["TGCN"] = TGCN(256, 256, (cfg.clip_frames, 8, 8), 10, 10).to(device)
-        self.sinkhorn = SinkhornDistance(eps=0.1, max_iter=5, reduction="mean")
+        self.sinkhorn = SinkhornDistance(eps=0.1, max_iter=5, reduction="mean")     # train_cardiac_uda.py:138
         self.dice = DiceLoss()
         self.ce = nn.CrossEntropyLoss()
         modules = [self.network, *self.aux.values()]
@@ -255,28 +275,39 @@ class UDAEngine:
                                              weight_decay=cfg.weight_decay, fused=device.type == "cuda")
 
     # ------------------------------------------------------------------------------------------
-    def capture_graphs(self, n_frames: int):
+    def _split(self, ns):
+        """BatchNorm segments for a [source | target] batch with ns source frames (GF.domain_split)."""
+        return GF.domain_split(ns if self.cfg.per_domain_bn else 0)
+
+    def _buffers(self):
+        return [b for m in [self.network, *self.aux.values()] for b in m.buffers()]
+
+    def capture_graphs(self, n_frames: int, n_source: int | None = None):
         """Capture the shape-static segments of the step -- the segmentation network, the p2 Grapher and
         the four discriminators, forward and backward -- as CUDA graphs (torch.cuda.make_graphed_callables),
         so that ~3 500 of the step's ~4 000 kernel launches are replayed by a dozen graph launches.  The
         data-dependent part (GModule: node sampling, matching) stays eager.  `n_frames` = source + target
-        frames per step on this rank (the segments are re-captured if it changes)."""
+        frames per step on this rank, `n_source` of them source frames (the segments are re-captured if they
+        change).  Buffers (BatchNorm running statistics, seed banks) are snapshotted before the warm-up / capture
+        executions on dummy inputs and restored afterwards: capturing leaves no trace in the model state."""
         cfg, dev = self.cfg, self.device
         if self.world > 1 and cfg.sync_bn:
             raise RuntimeError("cuda_graphs with SyncBatchNorm is not supported: use sync_bn=False")
-        ns = n_frames // 2
+        ns = n_frames // 2 if n_source is None else int(n_source)
+        bufs = self._buffers()
+        snapshot = [b.detach().clone() for b in bufs]
         x = torch.zeros(n_frames, 1, cfg.hw, cfg.hw, device=dev)
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16), self._split(ns):
             _, feats = self.network(x)
         # make_graphed_callables shares one memory pool between the graphs and relies on them being replayed in
         # the order of this tuple (forward) and in its reverse (backward): trunk -> Grapher -> head -> discriminators
         # forward, discriminators -> head -> Grapher -> trunk backward -- the order every step below keeps.
-        calls, samples, names = [self._trunk], [(x,)], ["trunk"]
+        calls, samples, names = [self._trunk_raw], [(x,)], ["trunk"]
         if cfg.graph_matching and cfg.vig_grapher:
             calls.append(self.aux["Grapher"])
             samples.append((torch.zeros_like(feats[0]).requires_grad_(),))
             names.append("Grapher")
-        calls.append(self._head)
+        calls.append(self._head_raw)
         samples.append(tuple(torch.zeros_like(f).requires_grad_() for f in feats))
         names.append("head")
         if cfg.graph_matching and cfg.discriminator:
@@ -288,7 +319,7 @@ class UDAEngine:
         del feats
         from . import _cabi
         before = _cabi.launch_count()
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16, cache_enabled=False):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16, cache_enabled=False), self._split(ns):
             graphed = torch.cuda.make_graphed_callables(tuple(calls), tuple(samples), num_warmup_iters=3,
                                                         allow_unused_input=True)
         # 3 warm-up executions + 1 capture of every segment's forward and backward
@@ -300,9 +331,12 @@ class UDAEngine:
                 self._head = g
             else:
                 self.aux[name] = g
+        with torch.no_grad():
+            for b, keep in zip(bufs, snapshot):
+                b.copy_(keep)
         self.grads.zero()
         self.graphed = True
-        self._graph_frames = n_frames
+        self._graph_frames = (n_frames, ns)
 
     def _autocast(self):
         return torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.cfg.bf16, cache_enabled=not self.graphed)
@@ -310,21 +344,60 @@ class UDAEngine:
     def seg_loss(self, logits, masks):
         return self.dice(logits, masks) + F.binary_cross_entropy_with_logits(logits, masks)
 
-    def forward_losses(self, frames_src, masks_src, frames_tgt, clips_shape=None):
-        """frames_* [F,1,H,W] (fp32, device), masks_src [F,nc,H,W] one-hot.  Returns the loss dict."""
-        cfg = self.cfg
-        ns = frames_src.shape[0]
-        losses = {}
+    def _prepare(self, frames_src, frames_tgt):
+        ns, n = frames_src.shape[0], frames_src.shape[0] + frames_tgt.shape[0]
         for m in self.aux.values():
             if isinstance(m, _JointDiscriminator):
-                if self.graphed and m.n_source not in (None, ns):
-                    raise RuntimeError("the source/target split changed after CUDA-graph capture")
                 m.n_source = ns
-        if cfg.cuda_graphs and not self.graphed:
-            self.capture_graphs(frames_src.shape[0] + frames_tgt.shape[0])
+        if self.cfg.cuda_graphs and not self.graphed:
+            self.capture_graphs(n, ns)
+        if self.graphed and self._graph_frames != (n, ns):
+            raise RuntimeError(f"the batch changed after CUDA-graph capture: {(n, ns)} vs {self._graph_frames}")
+        return ns
+
+    def _node_transport(self, nodes, losses):
+        """config 3: entropic optimal-transport distance between the two matched node sets (the reference's
+        SinkhornDistance(0.1, 5, 'mean'), train_cardiac_uda.py:138, applied as TGCN.py:281-283 applies it)."""
+        if self.cfg.sinkhorn_nodes and nodes[0].dim() == 2 and nodes[0].size(0) >= 6 and nodes[1].size(0) > 0:
+            losses["sinkhorn_loss"] = self.cfg.sinkhorn_weight * self.sinkhorn(nodes[0], nodes[1])[0]
+
+    def _temporal_losses(self, temporal):
+        """The temporal branch of the reference step (train_cardiac_uda.py:258-311): the [source | target] clips go
+        through the network in ONE call (one BatchNorm segment), the graph module runs on their pyramid with the RAW
+        target logits as score maps (Appendix A-12), and TGCN consumes the clip pyramids and the (detached) nodes.
+        `temp_seg_loss` (:283-290) never reaches `losses` in the reference, so the head runs without autograd.
+        Returns the scalar temporal_graph_loss (or None)."""
+        cfg = self.cfg
+        frames_temp, masks_temp, (b, t) = temporal
+        nst = masks_temp.shape[0]
         with self._autocast():
+            feats = list(self._trunk_raw(frames_temp))
+            with torch.no_grad():
+                logits = self._head_raw(*[f.detach() for f in feats])
+        pred_src = logits[:nst]
+        avail = (masks_temp.sum(dim=(1, 2, 3)) > 100).view(-1, 1, 1, 1)                 # :277, 283-290
+        targets = torch.where(avail, masks_temp, pred_src.to(masks_temp.dtype))
+        _, nodes, mid = self._gmodule.forward_joint(feats, nst, targets, logits[nst:])
+        self._gmodule.flush_seed_update()
+        total = sum(mid.values()) if mid else None
+        if nodes[0].numel() > 0 and nodes[0].dim() == 2:
+            graph_features = [f.reshape(b, t, *f.shape[1:]) for f in feats]             # :300-302
+            tl = self.aux["TGCN"](graph_features, (nodes[0].detach(), nodes[1].detach()), self.sinkhorn, self.ce,
+                                  (None, None), r=[8, 4, 2, 1])
+            tsum = sum(tl.values())
+            total = tsum if total is None else total + tsum
+        return total
+
+    def forward_losses(self, frames_src, masks_src, frames_tgt, temporal=None):
+        """frames_* [F,1,H,W] (fp32, device), masks_src [F,nc,H,W] one-hot.  Returns the loss dict (one autograd
+        graph; the reference order of train_cardiac_uda.py:223-311)."""
+        cfg = self.cfg
+        ns = self._prepare(frames_src, frames_tgt)
+        losses = {}
+        with self._autocast(), self._split(ns):
             feats = list(self._trunk(torch.cat([frames_src, frames_tgt], dim=0)))
             p2g = self.aux["Grapher"](feats[0]) if cfg.graph_matching and cfg.vig_grapher else None
+        with self._autocast():
             logits = self._head(*feats)
         pred_s, pred_t = logits[:ns], logits[ns:]
         losses["seg_loss"] = cfg.seg_weight * self.seg_loss(pred_s, masks_src)
@@ -345,6 +418,7 @@ class UDAEngine:
         with torch.cuda.stream(side) if side is not None else _NullCtx():
             # source frames first, target frames after: the joint entry points avoid slicing the pyramid
             _, nodes, mid = self._gmodule.forward_joint(feats, ns, masks_src, score_maps)
+            self._node_transport(nodes, mid)
         if cfg.discriminator:
             with self._autocast():
                 for i, lvl in enumerate(("p2", "p3", "p4", "p5")):
@@ -352,21 +426,20 @@ class UDAEngine:
         if side is not None:
             main.wait_stream(side)
         losses.update(mid)
-        if cfg.temporal_graph and clips_shape is not None and nodes[0].numel() > 0 and nodes[0].dim() == 2:
-            b, t = clips_shape                                                      # train_cardiac_uda.py:300-304
-            graph_features = [f.reshape(b, t, *f.shape[1:]) for f in feats]
-            tl = self.aux["TGCN"](graph_features, (nodes[0].detach(), nodes[1].detach()), self.sinkhorn, self.ce,
-                                  (None, None), r=[8, 4, 2, 1])
-            losses["temporal_graph_loss"] = sum(tl.values())
+        if cfg.temporal_graph and temporal is not None:
+            self._gmodule.flush_seed_update()
+            tloss = self._temporal_losses(temporal)
+            if tloss is not None:
+                losses["temporal_graph_loss"] = tloss
         return losses
 
-    def train_step(self, frames_src, masks_src, frames_tgt, clips_shape=None):
+    def train_step(self, frames_src, masks_src, frames_tgt, temporal=None):
         self.grads.zero()
         if self.cfg.phased_backward and self.cfg.graph_matching:
-            losses = self._phased_forward_backward(frames_src, masks_src, frames_tgt, clips_shape)
+            losses = self._phased_forward_backward(frames_src, masks_src, frames_tgt, temporal)
             total = sum(v.detach() for v in losses.values())
         else:
-            losses = self.forward_losses(frames_src, masks_src, frames_tgt, clips_shape)
+            losses = self.forward_losses(frames_src, masks_src, frames_tgt, temporal)
             total = sum(losses.values())
             total.backward()
             total = total.detach()
@@ -376,7 +449,7 @@ class UDAEngine:
             opt.step()
         return total, {k: v.detach() for k, v in losses.items()}
 
-    def _phased_forward_backward(self, frames_src, masks_src, frames_tgt, clips_shape=None):
+    def _phased_forward_backward(self, frames_src, masks_src, frames_tgt, temporal=None):
         """Same losses and gradients as forward_losses() + one backward(), issued in an order that keeps the GPU
         busy.  GModule is host-driven (two count read-backs, ~900 tiny launches forward, as many backward);
         in one autograd graph its launches sit between the pyramid and the discriminators on the CPU timeline
@@ -385,26 +458,21 @@ class UDAEngine:
           2. discriminators forward AND backward, then the head's backward          main stream, graph replays
           3. GModule forward and backward                                           side stream, while 2 runs
           4. pyramid gradients = head + discriminator + GModule parts; trunk backward   main stream
+          5. [temporal_graph] the clip branch: trunk on the clips, GModule + TGCN, their backward
         """
         cfg = self.cfg
-        ns = frames_src.shape[0]
+        ns = self._prepare(frames_src, frames_tgt)
         losses = {}
-        for m in self.aux.values():
-            if isinstance(m, _JointDiscriminator):
-                if self.graphed and m.n_source not in (None, ns):
-                    raise RuntimeError("the source/target split changed after CUDA-graph capture")
-                m.n_source = ns
-        if cfg.cuda_graphs and not self.graphed:
-            self.capture_graphs(frames_src.shape[0] + frames_tgt.shape[0])
         main = torch.cuda.current_stream()
         side = self._side_stream if cfg.overlap_streams else None
         if side is not None:
             side.wait_stream(main)          # inputs (e.g. the step's host->device copies) are ready for the side stream
-        with self._autocast():
+        with self._autocast(), self._split(ns):
             feats = list(self._trunk(torch.cat([frames_src, frames_tgt], dim=0)))
             tops = list(feats)
             if cfg.vig_grapher:
                 tops[0] = self.aux["Grapher"](feats[0])
+        with self._autocast():
             leaves_h = [f.detach().requires_grad_() for f in feats]
             logits = self._head(*leaves_h)
         # while the GPU runs the forward graphs: the source half of the sampler plan (needs the masks and the map
@@ -428,18 +496,12 @@ class UDAEngine:
                 losses[f"loss_adv_{lvl}"].backward()
             grads = [l.grad for l in leaves_d]
         seg.backward()                                                              # head only: stops at leaves_h
-        # 3. graph matching (and the temporal module that consumes its nodes) on the side stream
+        # 3. graph matching on the side stream
         leaves_g = [t.detach().requires_grad_() for t in tops]
         with torch.cuda.stream(side) if side is not None else _NullCtx():
             _, nodes, mid = self._gmodule.forward_joint(leaves_g, ns, masks_src, score_maps)
+            self._node_transport(nodes, mid)
             losses.update(mid)
-            if cfg.temporal_graph and clips_shape is not None and nodes[0].numel() > 0 and nodes[0].dim() == 2:
-                b, t = clips_shape                                                  # train_cardiac_uda.py:300-304
-                graph_features = [f.reshape(b, t, *f.shape[1:]) for f in leaves_g]
-                tl = self.aux["TGCN"](graph_features, (nodes[0].detach(), nodes[1].detach()), self.sinkhorn, self.ce,
-                                      (None, None), r=[8, 4, 2, 1])
-                losses["temporal_graph_loss"] = sum(tl.values())
-                mid = dict(mid, temporal_graph_loss=losses["temporal_graph_loss"])
             if mid:
                 torch.autograd.backward(list(mid.values()))
         if side is not None:
@@ -467,6 +529,12 @@ class UDAEngine:
             self._gmodule.flush_seed_update()
         if side is not None:
             main.wait_stream(side)
+        # 5. the clip branch (its own autograd graph: trunk parameters accumulate a second gradient)
+        if cfg.temporal_graph and temporal is not None:
+            tloss = self._temporal_losses(temporal)
+            if tloss is not None:
+                losses["temporal_graph_loss"] = tloss
+                tloss.backward()
         return losses
 
     @torch.no_grad()
@@ -491,9 +559,27 @@ def make_batch(cfg: EngineConfig, n_clips: int, frames: int, rank: int = 0, worl
     return x, masks
 
 
+def make_frame_batch(cfg: EngineConfig, n_src: int, n_tgt: int, rank: int = 0, seed: int = 0, pin: bool = False):
+    """Single-frame streams of the CardiacUDA / CAMUS trainers (train_cardiac_uda.py:189-192: source batch
+    2 x batch_size, target batch batch_size): (source frames [n_src,1,H,W], one-hot masks, target frames)."""
+    xs = synth.images(n_src, cfg.hw, seed=seed + 1000 * rank + 17)
+    xt = synth.images(n_tgt, cfg.hw, seed=seed + 1000 * rank + 29)
+    masks = synth.disc_masks(n_src, cfg.num_classes, cfg.hw)
+    if pin and torch.cuda.is_available():
+        xs, xt, masks = xs.pin_memory(), xt.pin_memory(), masks.pin_memory()
+    return xs, masks, xt
+
+
 def split_streams(clips_dev: torch.Tensor):
     """[b,1,H,W,t] on device -> (source frames, target frames, (b, t)); clip-major frame order."""
     b, c, h, w, t = clips_dev.shape
     frames = synth.flatten_clips(clips_dev)
     ns = (b // 2) * t
     return frames[:ns], frames[ns:], (b, t)
+
+
+def temporal_input(clips_dev: torch.Tensor, masks_dev: torch.Tensor):
+    """The `temporal` argument of train_step from device clips [b,1,H,W,t] (source clips first) and the source
+    clips' masks [b/2*t, nc, H, W]: (frames [b*t,1,H,W], masks, (b, t)) (train_cardiac_uda.py:272-276)."""
+    b, c, h, w, t = clips_dev.shape
+    return synth.flatten_clips(clips_dev), masks_dev, (b, t)

@@ -508,38 +508,72 @@ def maxpool3s2(x):
     return _MaxPool3s2.apply(x)
 
 
+# Per-domain BatchNorm statistics.  The reference trainers run the network on the source batch and on the target
+# batch as two separate train-mode calls (train_cardiac_uda.py:225, 234; train_camus_echo.py:208, 218): every
+# BatchNorm sees each domain's own batch statistics and updates its running statistics twice per step.  The engine
+# sends [source | target] through the convolutions as ONE batch; inside `domain_split(n_source_frames)` every fused
+# BatchNorm call treats the first n_source_frames images and the rest as two segments (statistics, running-stat
+# updates in source -> target order, backward sums), which is the two-call semantics at one-call cost.
+_BN_SPLIT = 0
+
+
+class domain_split:
+    def __init__(self, n_first):
+        self.n_first = int(n_first or 0)
+
+    def __enter__(self):
+        global _BN_SPLIT
+        self.prev, _BN_SPLIT = _BN_SPLIT, self.n_first
+        return self
+
+    def __exit__(self, *exc):
+        global _BN_SPLIT
+        _BN_SPLIT = self.prev
+        return False
+
+
+def bn_segments(n_images):
+    """Number of BatchNorm segments a batch of `n_images` is normalised in under the current domain_split."""
+    return 2 if 0 < _BN_SPLIT < n_images else 1
+
+
 class _BnAct(Function):
     """Training-mode fused BatchNorm2d (+ residual) (+ ReLU) on an NHWC map."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, momentum, eps, relu):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, nbt, momentum, eps, relu, split):
         _need_cuda(x, residual, gamma, beta)
         xc = _nhwc_view(x)
         N, C, H, W = xc.shape
         P = N * H * W
+        P_split = split * H * W if 0 < split < N else 0
+        nseg = 2 if P_split else 1
         rc = _nhwc_view(residual.to(xc.dtype)) if residual is not None else None
         g, b = _f32c(gamma), _f32c(beta)
         dev = x.device
         out = torch.empty_like(xc)
-        save = torch.empty((2, C), device=dev, dtype=torch.float32)
+        save = torch.empty((2, nseg, C), device=dev, dtype=torch.float32)
         nbytes = _cabi.lib().ge_bn_workspace_bytes(P, C)
         if nbytes == 0:
             raise _cabi.GraphEchoNativeError(f"fused BatchNorm does not support C={C}")
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        mask = None
+        if relu:
+            mask = torch.empty(_cabi.lib().ge_bn_relu_mask_bytes(P, C), device=dev, dtype=torch.uint8)
         es = xc.element_size()
-        call("ge_bn_fwd_train", ptr(xc), ptr(rc), ptr(g), ptr(b), ptr(running_mean), ptr(running_var),
-             c_float(momentum), c_float(eps), ptr(out), ptr(save[0]), ptr(save[1]), ptr(ws), c_size_t(nbytes),
-             _dtype_code(xc), c_longlong(P), C, int(relu), stream(),
-             work=(P * C * es * (3 + (1 if rc is not None else 0)), 8 * P * C))
-        ctx.save_for_backward(xc, out, g, save)
-        ctx.cfg = (P, C, float(eps), bool(relu), rc is not None, gamma.dtype, beta.dtype)
+        call("ge_bn_fwd_train", ptr(xc), ptr(rc), ptr(g), ptr(b), ptr(running_mean), ptr(running_var), ptr(nbt),
+             c_float(momentum), c_float(eps), ptr(out), ptr(save[0]), ptr(save[1]), ptr(mask), ptr(ws), c_size_t(nbytes),
+             _dtype_code(xc), c_longlong(P), c_longlong(P_split), C, int(relu), stream(),
+             work=(P * C * es * (2 + (1 if rc is not None else 0)), 8 * P * C))      # compulsory: x (+res) in, out
+        ctx.save_for_backward(xc, mask, g, save)
+        ctx.cfg = (P, P_split, C, bool(relu), rc is not None, gamma.dtype, beta.dtype)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        xc, out, g, save = ctx.saved_tensors
-        P, C, eps, relu, has_res, gdt, bdt = ctx.cfg
+        xc, mask, g, save = ctx.saved_tensors
+        P, P_split, C, relu, has_res, gdt, bdt = ctx.cfg
         d = _nhwc_view(dout.to(xc.dtype))
         dx = torch.empty_like(xc)
         dres = torch.empty_like(xc) if has_res else None
@@ -547,27 +581,32 @@ class _BnAct(Function):
         nbytes = _cabi.lib().ge_bn_workspace_bytes(P, C)
         ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
         es = xc.element_size()
-        call("ge_bn_bwd", ptr(d), ptr(out), ptr(xc), ptr(g), ptr(save[0]), ptr(save[1]), c_float(eps), ptr(dx),
-             ptr(dres), ptr(dgb[0]), ptr(dgb[1]), ptr(ws), c_size_t(nbytes), _dtype_code(xc), c_longlong(P), C,
-             int(relu), stream(), work=(P * C * es * (7 + (1 if has_res else 0)), 16 * P * C))
-        return dx, dres, dgb[0].to(gdt), dgb[1].to(bdt), None, None, None, None, None
+        call("ge_bn_bwd", ptr(d), ptr(mask), ptr(xc), ptr(g), ptr(save[0]), ptr(save[1]), ptr(dx),
+             ptr(dres), ptr(dgb[0]), ptr(dgb[1]), ptr(ws), c_size_t(nbytes), _dtype_code(xc), c_longlong(P),
+             c_longlong(P_split), C, int(relu), stream(),
+             work=(P * C * es * (3 + (1 if has_res else 0)) + (P * C // 8 if relu else 0), 16 * P * C))  # dy, x, mask in; dx (+dres) out
+        return dx, dres, dgb[0].to(gdt), dgb[1].to(bdt), None, None, None, None, None, None, None
 
 
 def bn_act(x, bn, residual=None, relu=True):
     """relu(BatchNorm2d(x) + residual) with `bn` an nn.BatchNorm2d (parameters / buffers are read and,
-    in training mode, updated exactly as the module would).  Other norm types (e.g. SyncBatchNorm)
-    fall back to the module itself."""
+    in training mode, updated exactly as the module would; under `domain_split` exactly as two calls on the two
+    halves would).  Other norm types (e.g. SyncBatchNorm) fall back to the module itself."""
+    split = _BN_SPLIT if 0 < _BN_SPLIT < x.shape[0] else 0
     if type(bn) is not torch.nn.BatchNorm2d or not bn.affine or (bn.training and bn.momentum is None):
-        y = bn(x)
+        if split and bn.training:
+            y = torch.cat([bn(x[:split]), bn(x[split:])], dim=0)
+        else:
+            y = bn(x)
         if residual is not None:
             y = y + residual
         return torch.relu(y) if relu else y
     if bn.training or not bn.track_running_stats:
         rm = bn.running_mean if bn.track_running_stats else None
         rv = bn.running_var if bn.track_running_stats else None
-        if bn.track_running_stats:
-            bn.num_batches_tracked.add_(1)
-        return _BnAct.apply(x, residual, bn.weight, bn.bias, rm, rv, float(bn.momentum), float(bn.eps), bool(relu))
+        nbt = bn.num_batches_tracked if bn.track_running_stats else None
+        return _BnAct.apply(x, residual, bn.weight, bn.bias, rm, rv, nbt, float(bn.momentum), float(bn.eps), bool(relu),
+                            int(split))
     # inference: a per-channel affine map -- differentiable through ordinary autograd if anyone asks
     if torch.is_grad_enabled() and (x.requires_grad or bn.weight.requires_grad):
         y = torch.nn.functional.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)

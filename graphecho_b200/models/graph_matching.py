@@ -110,6 +110,9 @@ class GModule(nn.Module):
         self.node_dis_2 = _ln_mlp([256, 256, 256, 256, 1], final_ln=False)         # keys 0, 3, 6, 9
         self.loss_fn = nn.BCEWithLogitsLoss()
         self._init_weight()
+        # the seed banks are updated on a private stream (update_seed): anything that reads them through
+        # state_dict() (checkpoints, buffer broadcasts) first joins that stream
+        self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module._sync_seed_stream())
 
     def _init_weight(self):
         seqs = [self.node_dis_2, self.node_cls_middle, self.head_in_ln, [self.seed_project_left]]
@@ -308,8 +311,11 @@ class GModule(nn.Module):
             # mask instead of a boolean gather (no host sync): mean focal loss over them / their sum
             diff = 1.0 - samef
             a, g = self.matching_loss.alpha, self.matching_loss.gamma
-            fp_elem = -(1 - a) * M ** g * torch.log(1 - M)
-            fp_loss = (fp_elem * diff).sum() / diff.sum() / (M * diff).sum().detach()
+            # mask BEFORE the log: a same-class entry that saturates to 1.0 would otherwise contribute
+            # -inf * 0 = NaN (forward and backward); the reference gathers the different-class entries only
+            Mfp = torch.where(same, torch.zeros_like(M), M)
+            fp_elem = -(1 - a) * Mfp ** g * torch.log(1 - Mfp)
+            fp_loss = fp_elem.sum() / diff.sum() / Mfp.sum().detach()
             return tp_loss + fp_loss, M
         if self.matching_cfg == "m2m":
             return self.matching_loss(M.sigmoid(), same.float()).mean(), M

@@ -228,7 +228,9 @@ def _conv_bn_train(x, conv, bn, residual=None):
                   residual=residual, relu=False)
     if conv.bias is not None and bn.track_running_stats:
         with torch.no_grad():
-            bn.running_mean.add_(conv.bias.detach().to(bn.running_mean.dtype), alpha=float(bn.momentum))
+            # one running-mean update per BatchNorm segment (GF.domain_split): 1 - (1-m)^nseg of the bias in total
+            share = 1.0 - (1.0 - float(bn.momentum)) ** GF.bn_segments(x.shape[0])
+            bn.running_mean.add_(conv.bias.detach().to(bn.running_mean.dtype), alpha=share)
     return y
 
 

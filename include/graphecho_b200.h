@@ -185,22 +185,30 @@ int ge_seg_tail_bwd(const float* dlogits, const void* s2, const void* s3, const 
 /* ---- fused BatchNorm2d (+ residual add) (+ ReLU) on NHWC maps ---------------------------------
  * nn.BatchNorm2d + `out += identity` + nn.ReLU of Bottleneck.forward / the ResNet stem / the VGG16
  * blocks (models/fpnseg.py:192-212, 251-255, 27-142).  x, residual (or NULL), out: [P,C] with
- * P = N*H*W, in `dtype`; gamma, beta, running_*, save_* fp32 [C].  Training mode uses batch statistics
- * (biased variance), updates running_* with `momentum` (unbiased variance) exactly as nn.BatchNorm2d,
- * and saves mean / rstd for the backward.  Two-stage deterministic reductions through `workspace`. */
+ * P = N*H*W, in `dtype`; gamma, beta, running_* fp32 [C].  Training mode uses batch statistics
+ * (biased variance), updates running_* with `momentum` (unbiased variance) and num_batches_tracked exactly as
+ * nn.BatchNorm2d, and saves mean / rstd for the backward.  Two-stage deterministic reductions through `workspace`.
+ * P_split: 0 < P_split < P splits the batch into two SEGMENTS [0,P_split) and [P_split,P) with their own batch
+ * statistics and one running-stat update each, in that order -- the semantics of the reference trainer's two
+ * separate network calls on the source and the target batch (train_cardiac_uda.py:225, 234) for a batch that
+ * holds both.  save_mean / save_rstd are then [2][C] (else [1][C]).
+ * relu_mask (ge_bn_relu_mask_bytes(P,C) bytes; may be NULL when relu == 0): 1-bit-per-element ReLU mask written by
+ * the forward and consumed by the backward, which therefore never re-reads `out`. */
 size_t ge_bn_workspace_bytes(long long P, int C);
+size_t ge_bn_relu_mask_bytes(long long P, int C);
 int ge_bn_fwd_train(const void* x, const void* residual, const float* gamma, const float* beta,
-                    float* running_mean, float* running_var, float momentum, float eps,
-                    void* out, float* save_mean, float* save_rstd, void* workspace, size_t workspace_bytes,
-                    int dtype, long long P, int C, int relu, ge_stream_t stream);
+                    float* running_mean, float* running_var, long long* num_batches_tracked,
+                    float momentum, float eps, void* out, float* save_mean, float* save_rstd,
+                    void* relu_mask, void* workspace, size_t workspace_bytes,
+                    int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream);
 int ge_bn_fwd_eval(const void* x, const void* residual, const float* gamma, const float* beta,
                    const float* running_mean, const float* running_var, float eps, void* out,
                    int dtype, long long P, int C, int relu, ge_stream_t stream);
 /* dx [P,C]; dres [P,C] or NULL (gradient of the residual input); dgamma, dbeta fp32 [C]. */
-int ge_bn_bwd(const void* dy, const void* out, const void* x, const float* gamma,
-              const float* mean, const float* rstd, float eps, void* dx, void* dres,
+int ge_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float* gamma,
+              const float* mean, const float* rstd, void* dx, void* dres,
               float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-              int dtype, long long P, int C, int relu, ge_stream_t stream);
+              int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream);
 
 /* ---- update_seed: spectral bipartition ------------------------------------------------------
  * What GModule.update_seed asks sklearn's SpectralClustering(2, affinity='nearest_neighbors',
