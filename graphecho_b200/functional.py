@@ -447,7 +447,7 @@ class _GnReluUpsample(Function):
         dx = torch.empty_like(xc)
         call("ge_gn_relu_upsample_bwd", ptr(d), ptr(xc), ptr(mean), ptr(rstd), ptr(g), ptr(b), ptr(None),
              ptr(S[0]), ptr(S[1]), ptr(S[2]), ptr(S[3]), ptr(dx), _dtype_code(xc), N, h, w, h, w, C, cpg, stream(),
-             work=(N * C * es * 4 * h * w, 20 * N * C * h * w))
+             work=(N * C * es * 3 * h * w, 20 * N * C * h * w))          # compulsory: dy, x in; dx out
         dpb = None
         if csum is not None:
             # d/d pre_bias = sum_{n,hw} dx, in closed form from the [N,C] arrays of the two kernels (no pass over dx):

@@ -227,6 +227,15 @@ def gen_tgcn(R):
     save("tgcn", out)
 
 
+def gen_pvig(R):
+    """pvig_ti_224_gelu (DeepGCN): eval-mode logits for a seeded 224x224 input."""
+    net = fill_module(_quiet(R["vig"].pvig_ti_224_gelu), scale=0.7).eval()
+    x = torch.rand(2, 3, 224, 224, generator=torch.Generator().manual_seed(41))
+    with torch.no_grad():
+        logits = _quiet(net, x)
+    save("pvig", dict(seed=41, shape=[2, 3, 224, 224], logits=logits))      # x = torch.rand(shape, Generator(seed))
+
+
 def gen_state_contract(R):
     """state_dict keys / shapes of every hot-path module, as the reference builds them."""
     import json
@@ -263,6 +272,7 @@ def main():
     gen_fpn(R)
     gen_gmodule(R)
     gen_tgcn(R)
+    gen_pvig(R)
 
 
 if __name__ == "__main__":

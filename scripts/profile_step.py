@@ -13,7 +13,7 @@ clips, masks = make_batch(cfg, 8, 32)
 clips, masks = clips.to(dev), masks.to(dev)
 def step():
     fs, ft, shape = split_streams(clips)
-    return eng.train_step(fs, masks, ft, shape)[0]
+    return eng.train_step(fs, masks, ft)[0]
 for _ in range(4): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:

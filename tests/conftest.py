@@ -47,3 +47,35 @@ def _exact_fp32():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     yield
+
+
+@pytest.fixture()
+def fixed_normal():
+    """Replace torch.normal / torch.randn_like by one deterministic, device-independent pattern, so that the node
+    hallucination of GModule (graph_matching.py:438-463: classes present in one domain only are completed with random
+    draws around the seed bank) produces the SAME nodes in the CUDA engine and in the CPU oracle, and every loss
+    downstream of it can be compared exactly instead of statistically."""
+    real_normal, real_randn_like = torch.normal, torch.randn_like
+
+    def pattern(shape, device):
+        n = 1
+        for s_ in shape:
+            n *= int(s_)
+        t = torch.arange(n, device=device, dtype=torch.float32) * 0.6180339887
+        return ((t - t.floor()) * 2.0 - 1.0).reshape(tuple(shape))
+
+    def normal(mean=0.0, std=1.0, size=None, generator=None, **kw):
+        if torch.is_tensor(mean):
+            return mean + std * pattern(mean.shape, mean.device)
+        if torch.is_tensor(std):
+            return mean + std * pattern(std.shape, std.device)
+        return mean + std * pattern(size, "cpu")
+
+    def randn_like(t, **kw):
+        return pattern(t.shape, t.device)
+
+    torch.normal, torch.randn_like = normal, randn_like
+    try:
+        yield
+    finally:
+        torch.normal, torch.randn_like = real_normal, real_randn_like

@@ -167,6 +167,25 @@ def _check_knn(edge, x, y, k, dilation, rel=None):
     return float(mism.float().mean())
 
 
+@pytest.mark.parametrize("P1,P2,B", [(250, 301, 1), (320, 204, 2)])
+def test_sinkhorn_distance_large_node_sets(dev, P1, P2, B):
+    """Node sets of the graph module (~200-320 rows, config 3): the P1 x P2 matrices exceed one CTA's shared memory
+    and live in their global arrays instead (`spill`) -- cost, plan, cost matrix and the gradients vs the oracle."""
+    torch.manual_seed(P1)
+    x = (torch.randn(B, P1, 256) * 0.5).requires_grad_()
+    y = (torch.randn(B, P2, 256) * 0.5 + 0.1).requires_grad_()
+    cost, pi, C, _ = G.sinkhorn_distance(x, y, 0.1, 5, "mean")
+    cost.backward()
+    xd, yd = x.detach().to(dev).requires_grad_(), y.detach().to(dev).requires_grad_()
+    c2, pi2, C2, _ = GF.sinkhorn_distance(xd, yd, 0.1, 5)
+    c2.mean().backward()
+    close(C2, C, rtol=1e-4, atol=1e-4)
+    close(c2.mean(), cost, rtol=1e-3, atol=1e-5)
+    close(pi2, pi, rtol=2e-3, atol=1e-7)
+    close(xd.grad, x.grad, rtol=5e-3, atol=1e-6 + 1e-3 * float(x.grad.abs().max()))
+    close(yd.grad, y.grad, rtol=5e-3, atol=1e-6 + 1e-3 * float(y.grad.abs().max()))
+
+
 def test_knn_golden(dev, golden):
     g = golden("vig")
     x, y, rel = g["x"], g["y"], g["rel"]
@@ -522,6 +541,56 @@ def test_bn_act_train_and_eval(dev, C, hw, res, relu, dtype):
         ref_e = torch.relu(y) if relu else y
         out_e = GF.bn_act(_cl(x, dev, dtype), our_bn, residual=None if not res else _cl(r, dev, dtype), relu=relu)
     close(out_e, ref_e, rtol=2e-2 if lo else 1e-4, atol=3e-2 if lo else 2e-5)
+
+
+@pytest.mark.parametrize("C,hw,N,ns,res,relu,dtype", [(64, 7, 5, 3, False, True, torch.float32),     # P_split = 147: a thread straddles
+                                                       (256, 14, 6, 2, True, True, torch.float32),
+                                                       (2048, 4, 4, 1, True, True, torch.float32),
+                                                       (512, 7, 5, 4, False, False, torch.float32),
+                                                       (256, 28, 8, 4, True, True, torch.bfloat16),
+                                                       (64, 56, 4, 2, False, True, torch.bfloat16)])
+def test_bn_act_domain_split_equals_two_calls(dev, C, hw, N, ns, res, relu, dtype):
+    """Per-domain statistics: one fused call on the [source | target] batch under GF.domain_split(ns) == two separate
+    nn.BatchNorm2d calls, source first (train_cardiac_uda.py:225, 234): outputs, all gradients (gamma / beta gradients
+    accumulate over the two calls), running statistics after TWO momentum updates, num_batches_tracked == 2."""
+    import copy
+    torch.manual_seed(C + hw + ns)
+    x = torch.cat([torch.randn(ns, C, hw, hw) * 1.4 + 0.3, torch.randn(N - ns, C, hw, hw) * 0.6 - 0.5]).to(dtype).float()
+    r = torch.randn(N, C, hw, hw).to(dtype).float() if res else None
+    ref_bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        ref_bn.weight.copy_(1 + 0.1 * torch.randn(C)); ref_bn.bias.copy_(0.1 * torch.randn(C))
+        ref_bn.running_mean.copy_(0.05 * torch.randn(C)); ref_bn.running_var.copy_(1 + 0.1 * torch.rand(C))
+    our_bn = copy.deepcopy(ref_bn).to(dev)
+    xo = x.clone().requires_grad_()
+    ro = r.clone().requires_grad_() if res else None
+    y = torch.cat([ref_bn(xo[:ns]), ref_bn(xo[ns:])])
+    if res:
+        y = y + ro
+    ref = torch.relu(y) if relu else y
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    xd = _cl(x, dev, dtype).requires_grad_()
+    rd = _cl(r, dev, dtype).requires_grad_() if res else None
+    with GF.domain_split(ns):
+        out = GF.bn_act(xd, our_bn, residual=rd, relu=relu)
+    lo = dtype == torch.bfloat16
+    close(out, ref, rtol=2e-2 if lo else 1e-4, atol=3e-2 if lo else 2e-5)
+    (out * W.to(dev).to(dtype)).sum().backward()          # outside the context: the split travels with the autograd node
+    close(xd.grad, xo.grad, rtol=5e-2 if lo else 2e-3, atol=5e-2 if lo else 2e-4)
+    if res:
+        close(rd.grad, ro.grad, rtol=2e-2 if lo else 1e-5, atol=2e-2 if lo else 1e-6)
+    scale = float(ref_bn.weight.grad.abs().max())
+    close(our_bn.weight.grad, ref_bn.weight.grad, rtol=3e-2 if lo else 1e-3, atol=(3e-2 if lo else 1e-4) * scale)
+    close(our_bn.bias.grad, ref_bn.bias.grad, rtol=3e-2 if lo else 1e-3, atol=(3e-2 if lo else 1e-4) * scale)
+    close(our_bn.running_mean, ref_bn.running_mean, rtol=1e-4, atol=1e-5)
+    close(our_bn.running_var, ref_bn.running_var, rtol=1e-4, atol=1e-5)
+    assert int(our_bn.num_batches_tracked) == 2
+    # and the whole-batch call is NOT the same thing (the two domains have different statistics)
+    with torch.no_grad():
+        whole = GF.bn_act(_cl(x, dev, dtype), copy.deepcopy(ref_bn).to(dev).train(), residual=None if not res else _cl(r, dev, dtype),
+                          relu=relu)
+    assert (whole.float().cpu() - ref).abs().max() > 0.05
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

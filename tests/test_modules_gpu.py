@@ -14,7 +14,8 @@ from graphecho_b200.models import fpnseg, graph_matching, TGCN as tgcn_mod, vig,
 from graphecho_b200.utils.sinkhorn_distance import SinkhornDistance
 from graphecho_b200.utils.losses import DiceLoss
 from oracle.detfill import fill_module
-from oracle import fpn_ops as FP
+from oracle import fpn_ops as FP, vig_ops as V
+from oracle.params import make_params
 
 pytestmark = pytest.mark.gpu
 
@@ -128,6 +129,55 @@ def test_grapher_node_major_path_equals_reference_layout_path(dev, r):
         close(a, b, rtol=2e-3, atol=1e-5)
 
 
+@pytest.mark.parametrize("dtype,r", [(torch.float32, 1), (torch.float32, 2), (torch.bfloat16, 1)])
+def test_grapher_benched_shape_against_the_oracle(dev, dtype, r):
+    """The benched Grapher -- 256 channels, k=9, N = 784 nodes (the 28x28 p2 map of a 112x112 frame), node-major route on
+    the tcgen05 k-NN kernel -- DIRECTLY against oracle.vig_ops.grapher (not against the repo's other route): output,
+    input gradient, parameter gradients, BatchNorm running statistics.  A k-NN near-tie resolved the other way swaps one
+    neighbour of one node, i.e. changes a handful of max-relative features: the comparison is a relative Frobenius
+    error plus a bound on the fraction of visibly different output elements.  bf16: the autocast path bench.py runs."""
+    torch.manual_seed(3)
+    B, C, H = 3, 256, 28
+    x = torch.randn(B, C, H, H) * 0.8
+    P = make_params("grapher256", fill_prefix="grapher.", requires_grad=True)
+    xo = x.clone().requires_grad_()
+    ref, e_ref = V.grapher(xo, P, "", k=9, dilation=1, r=r, norm="batch", act="gelu", training=True, return_edges=True)
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    gr = fill_module(vig.Grapher(C, 9, 1, "mr", "gelu", "batch", True, False, 0.0, r, H * H, 0.0, False),
+                     prefix="grapher.").to(dev).train()
+    assert vig.Grapher._node_major_ok(gr, torch.empty(B, C, H, H, device=dev))      # the benched route applies
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        out = gr(xd)
+    assert out.dtype == dtype
+    (out.float() * W.to(dev)).sum().backward()
+    lo = dtype == torch.bfloat16
+    relclose(out, ref, 3e-2 if lo else 2e-3)
+    bad = ((out.detach().float().cpu() - ref.detach()).abs() > (0.1 if lo else 1e-2) * ref.detach().abs().max()).float().mean()
+    assert bad < 1e-3, float(bad)
+    relclose(xd.grad, xo.grad, 6e-2 if lo else 5e-3)
+    relclose(gr.fc1[0].weight.grad, P["fc1.0.weight"].grad, 6e-2 if lo else 5e-3)
+    relclose(gr.graph_conv.gconv.nn[0].weight.grad, P["graph_conv.gconv.nn.0.weight"].grad, 6e-2 if lo else 5e-3)
+    relclose(gr.fc2[0].weight.grad, P["fc2.0.weight"].grad, 6e-2 if lo else 5e-3)
+    close(gr.fc2[1].running_mean, P["fc2.1.running_mean"], rtol=2e-2 if lo else 1e-3, atol=2e-2 if lo else 1e-4)
+    close(gr.fc1[1].running_var, P["fc1.1.running_var"], rtol=2e-2 if lo else 1e-3, atol=2e-2 if lo else 1e-4)
+
+
+def test_pvig_forward_matches_the_reference(dev, golden):
+    """DeepGCN through the pvig_ti_224_gelu factory (vig.py:586-751: Stem, 12 Grapher + FFN blocks over 4 stages with
+    relative position bias and r = 4/2/1/1 pooling, Downsample, prediction head), eval mode, against the logits the
+    unmodified reference produced for the same name-keyed weights."""
+    g = golden("pvig")
+    net = fill_module(quiet(vig.pvig_ti_224_gelu), scale=0.7).to(dev).eval()
+    x = torch.rand(*g["shape"], generator=torch.Generator().manual_seed(g["seed"]))
+    with torch.no_grad():
+        out = quiet(net, x.to(dev))
+    assert out.shape == g["logits"].shape
+    relclose(out, g["logits"], 2e-3)
+    assert torch.equal(out.argmax(1).cpu(), g["logits"].argmax(1))
+
+
 @pytest.mark.parametrize("bb,nc,hw", [("resnet", 1, 112), ("VGG16", 3, 64)])
 def test_fpn_matches_reference(dev, golden, bb, nc, hw):
     g = golden("fpn")
@@ -181,8 +231,11 @@ def test_discriminator(dev, golden):
     close(m.cls_logits.weight.grad, d["dcls"], rtol=5e-3, atol=1e-6)
 
 
-@pytest.mark.parametrize("backend", ["sklearn"])
+@pytest.mark.parametrize("backend", ["sklearn", "device"])
 def test_gmodule_train_step(dev, golden, backend):
+    """`device` = the on-GPU spectral bipartition bench.py runs: same-step losses, nodes and gradients are identical by
+    construction (update_seed only writes the seed banks); the banks themselves are compared with the reference's
+    (sklearn) banks -- a different eigen-solver may assign a few boundary points to the other cluster."""
     g = golden("gmodule")
     B, hw, nc = g["B"], g["hw"], g["nc"]
     gm = no_dropout(fill_module(quiet(graph_matching.GModule, 256, nc, dev))).to(dev).train()
@@ -197,8 +250,13 @@ def test_gmodule_train_step(dev, golden, backend):
         close(losses[k], g["losses"][k], rtol=2e-3, atol=1e-6)
     close(n1, g["n1"], rtol=2e-3, atol=2e-4)
     close(n2, g["n2"], rtol=2e-3, atol=2e-4)
-    close(gm.sr_seed, g["sr_seed"], rtol=2e-3, atol=2e-4)
-    close(gm.tg_seed, g["tg_seed"], rtol=2e-3, atol=2e-4)
+    gm.state_dict()                                   # joins the seed stream
+    if backend == "sklearn":
+        close(gm.sr_seed, g["sr_seed"], rtol=2e-3, atol=2e-4)
+        close(gm.tg_seed, g["tg_seed"], rtol=2e-3, atol=2e-4)
+    else:
+        relclose(gm.sr_seed, g["sr_seed"], 5e-2)
+        relclose(gm.tg_seed, g["tg_seed"], 5e-2)
     sum(losses.values()).backward()
     close(fs[3].grad, g["dfs3"], rtol=1e-2, atol=1e-7)
     close(fs[0].grad.abs().sum(), g["dfs0_abs"], rtol=1e-2, atol=1e-7)
