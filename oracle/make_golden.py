@@ -227,13 +227,37 @@ def gen_tgcn(R):
     save("tgcn", out)
 
 
+def stage_probe(x):
+    """A small deterministic sub-sample of a [B,C,H,W] activation (<= 2x8x4x4 values) + its mean / std."""
+    B, C, H, W = x.shape
+    sub = x[:, ::max(1, C // 8), ::max(1, H // 4), ::max(1, W // 4)][:, :8, :4, :4].contiguous()
+    return dict(sub=sub.clone(), mean=x.mean().clone(), std=x.std().clone())
+
+
 def gen_pvig(R):
-    """pvig_ti_224_gelu (DeepGCN): eval-mode logits for a seeded 224x224 input."""
+    """pvig_ti_224_gelu (DeepGCN), eval mode, seeded 224x224 input.  Two kinds of records:
+    * chained: a probe of the activation after the stem (+pos_embed) and after every backbone element, and the logits;
+    * teacher-forced, for the elements of stages 3-4 (dilated k-NN: the strided pick over the distance-sorted list makes
+      the selected set sensitive to ANY adjacent near-tie, so one fp32 round-off flip early on is amplified block by
+      block in a chained run): the reference element's input (image 0, rounded to fp16) and a probe of ITS output for
+      exactly that input; plus the pooled feature vector and the logits of the prediction head."""
     net = fill_module(_quiet(R["vig"].pvig_ti_224_gelu), scale=0.7).eval()
     x = torch.rand(2, 3, 224, 224, generator=torch.Generator().manual_seed(41))
+    stages, forced = [], {}
     with torch.no_grad():
+        h = net.stem(x) + net.pos_embed
+        stages.append(stage_probe(h))
+        for i, blk in enumerate(net.backbone):
+            if i >= 6:
+                inp = h[:1].half()
+                forced[i] = dict(inp=inp, out=stage_probe(_quiet(blk, inp.float())))
+            h = _quiet(blk, h)
+            stages.append(stage_probe(h))
+        pooled = torch.nn.functional.adaptive_avg_pool2d(h, 1)
         logits = _quiet(net, x)
-    save("pvig", dict(seed=41, shape=[2, 3, 224, 224], logits=logits))      # x = torch.rand(shape, Generator(seed))
+        head = net.prediction(pooled).squeeze(-1).squeeze(-1)
+    save("pvig", dict(seed=41, shape=[2, 3, 224, 224], logits=logits, stages=stages, forced=forced,
+                      pooled=pooled, head_logits=head))   # x = torch.rand(shape, Generator(seed))
 
 
 def gen_state_contract(R):
