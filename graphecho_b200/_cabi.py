@@ -55,9 +55,14 @@ _SIGNATURES = {
     "ge_seg_tail_fwd": (c_int, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P]),
     "ge_bn_workspace_bytes": (c_size_t, [L, I]),
     "ge_bn_relu_mask_bytes": (c_size_t, [L, I]),
+    "ge_bn_set_path": (c_int, [I]),
     "ge_bn_fwd_train": (c_int, [P, P, P, P, P, P, P, F, F, P, P, P, P, P, Z, I, L, L, I, I, P]),
     "ge_bn_fwd_eval": (c_int, [P, P, P, P, P, P, F, P, I, L, I, I, P]),
     "ge_bn_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, Z, I, L, L, I, I, P]),
+    "ge_seg_loss_workspace_bytes": (c_size_t, [I, I, I]),
+    "ge_seg_loss_fwd": (c_int, [P, P, P, P, P, Z, I, I, I, F, P]),
+    "ge_seg_loss_bwd": (c_int, [P, P, P, P, P, I, I, I, P]),
+    "ge_mask_boxes": (c_int, [P, P, I, I, I, I, I, P]),
     "ge_spectral_bipartition_max_points": (c_int, []),
     "ge_spectral_bipartition": (c_int, [P, P, I, I, I, I, P]),
     "ge_seg_tail_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P]),

@@ -20,6 +20,7 @@
 // [source | target] batch through the convolutions; `P_split` (pixels of the first segment; 0 = one segment) makes
 // the statistics, the running-stat updates (source first, then target) and the backward sums per segment.
 #include "common.cuh"
+#include "batch_norm_coop.cuh"
 #include "../../include/graphecho_b200.h"
 
 namespace {
@@ -91,52 +92,48 @@ bn_partial_stats_kernel(const T* __restrict__ x, const float* __restrict__ shift
     }
 }
 
-// Sum the per-CTA partials of 32 channels with FL part-lanes (CTA = 32*FL threads, grid = ceil(C/32)).  The loop is
-// latency-bound (one L2 round trip per row), so every thread keeps 8 independent rows (16 loads) in flight and
-// FL = 32 lanes share the rows: <= 3 trips at 592 partials.  Every thread of the CTA must call; the result is valid
-// in the threads with lane_p == 0.
-constexpr int FL = 32;
+// Sum the per-CTA partials of FCH channels with FLN part-lanes (CTA = FCH*FLN threads, grid = ceil(C/FCH)).  The
+// reduction is latency-bound (L2 round trips), so it is spread over many small CTAs (C/8 of them: 32 for C = 256) and
+// every thread issues all of its (<= 5 x 2) loads before the first add.  Every thread of the CTA must call; the result
+// is valid in the threads with lane_p == 0.
+constexpr int FCH = 8, FLN = 64, FROWS = 5;      // up to FLN*FROWS = 320 partial rows per segment without a second trip
 
 __device__ __forceinline__ void reduce_parts(const float* __restrict__ part, int nparts, int C, int c, int lane_p,
-                                             float (*sh)[2][33], float& sa, float& sb) {
+                                             float (*sh)[2][FCH], float& sa, float& sb) {
     float a = 0.f, b = 0.f;
     if (c < C) {
-        int q = lane_p;
-        for (; q + 7 * FL < nparts; q += 8 * FL) {
-            float va[8], vb[8];
+        for (int q0 = lane_p; q0 < nparts; q0 += FLN * FROWS) {
+            float va[FROWS], vb[FROWS];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                va[u] = part[(size_t)(q + FL * u) * 2 * C + c];
-                vb[u] = part[(size_t)(q + FL * u) * 2 * C + C + c];
+            for (int u = 0; u < FROWS; ++u) {
+                const int q = q0 + FLN * u;
+                va[u] = q < nparts ? part[(size_t)q * 2 * C + c] : 0.f;
+                vb[u] = q < nparts ? part[(size_t)q * 2 * C + C + c] : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { a += va[u]; b += vb[u]; }
-        }
-        for (; q < nparts; q += FL) {
-            a += part[(size_t)q * 2 * C + c];
-            b += part[(size_t)q * 2 * C + C + c];
+            for (int u = 0; u < FROWS; ++u) { a += va[u]; b += vb[u]; }
         }
     }
     __syncthreads();                 // a previous call's readers are done with sh
-    sh[lane_p][0][threadIdx.x & 31] = a;
-    sh[lane_p][1][threadIdx.x & 31] = b;
+    sh[lane_p][0][threadIdx.x % FCH] = a;
+    sh[lane_p][1][threadIdx.x % FCH] = b;
     __syncthreads();
     sa = 0.f; sb = 0.f;
     if (lane_p == 0) {
-#pragma unroll
-        for (int q = 0; q < FL; ++q) { sa += sh[q][0][threadIdx.x & 31]; sb += sh[q][1][threadIdx.x & 31]; }
+#pragma unroll 8
+        for (int q = 0; q < FLN; ++q) { sa += sh[q][0][threadIdx.x % FCH]; sb += sh[q][1][threadIdx.x % FCH]; }
     }
 }
 
 // ---- stage 2 (forward): batch mean / rstd per segment, running statistics (nn.BatchNorm2d semantics, one update
 // per segment in segment order), num_batches_tracked += segments ------------------------------------------------
-__global__ void __launch_bounds__(32 * FL)
+__global__ void __launch_bounds__(FCH * FLN)
 bn_finalize_stats_kernel(const float* __restrict__ part, SegPlan sp, const float* __restrict__ shift_src,
                          float* __restrict__ save_mean, float* __restrict__ save_rstd,
                          float* __restrict__ running_mean, float* __restrict__ running_var,
                          long long* __restrict__ num_batches_tracked, int C, float eps, float momentum) {
-    __shared__ float sh[FL][2][33];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane8 = threadIdx.x >> 5;
+    __shared__ float sh[FLN][2][FCH];
+    const int c = blockIdx.x * FCH + (threadIdx.x % FCH), lane8 = threadIdx.x / FCH;
     const bool owner = lane8 == 0 && c < C;
     const int nseg = sp.nseg();
     const float shift = c < C ? shift_src[c] : 0.f;          // read before the running mean is updated below
@@ -172,7 +169,7 @@ bn_finalize_stats_kernel(const float* __restrict__ part, SegPlan sp, const float
 constexpr int FPIX4 = 4;
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_apply_fwd4_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ mean,
                      const float* __restrict__ rstd_or_var, const float* __restrict__ gamma,
                      const float* __restrict__ beta, T* __restrict__ out, unsigned short* __restrict__ mask,
@@ -285,11 +282,11 @@ bn_partial_bwd_kernel(const T* __restrict__ dy, const unsigned short* __restrict
 
 // ---- backward stage 2: per segment S1 = sum dyr, S2 = sum dyr*xhat -> seg_sums [2][nseg][C]; dbeta = sum_s S1,
 // dgamma = sum_s S2 ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * FL)
+__global__ void __launch_bounds__(FCH * FLN)
 bn_finalize_bwd_kernel(const float* __restrict__ part, SegPlan sp, float* __restrict__ seg_sums,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
-    __shared__ float sh[FL][2][33];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane8 = threadIdx.x >> 5;
+    __shared__ float sh[FLN][2][FCH];
+    const int c = blockIdx.x * FCH + (threadIdx.x % FCH), lane8 = threadIdx.x / FCH;
     const bool owner = lane8 == 0 && c < C;
     const int nseg = sp.nseg();
     float ta = 0.f, tb = 0.f;
@@ -313,7 +310,7 @@ constexpr int BPIX4 = 4;
 static_assert(BPIX4 == FPIX4, "the ReLU mask layout is shared by the forward and backward apply kernels");
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_apply_bwd4_kernel(const T* __restrict__ dy, const unsigned short* __restrict__ mask, const T* __restrict__ x,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ seg_sums,
@@ -374,7 +371,7 @@ bn_apply_bwd4_kernel(const T* __restrict__ dy, const unsigned short* __restrict_
 int bn_chunks(long long P, int C) {
     const int nPL = BN_THREADS / (C / 8);
     long long want = P / ((long long)nPL * 8);           // >= 8 pixels per pixel-lane
-    const long long cap = (long long)ge::sm_count() * 4;
+    const long long cap = (long long)ge::sm_count() * 2;       // <= 296 partial rows: one trip of the finalize lanes
     if (want > cap) want = cap;
     if (want < 2) want = 2;                              // room for one chunk per segment
     return (int)want;
@@ -404,12 +401,52 @@ bool bn_shape_ok(int C) { return C % 8 == 0 && C / 8 <= BN_THREADS && BN_THREADS
 
 size_t bn_smem(int C) { return (size_t)2 * (BN_THREADS / (C / 8)) * C * sizeof(float); }
 
+// 0 / 1 = three-kernel streaming path (default), 2 = single-launch cooperative kernels where the map fits on chip.
+// The cooperative path is NOT the default: alone it is no faster (15-17 us vs 14-16 us at 4-6 MB, 29 vs 31 us at 26 MB:
+// two grid barriers + an in-kernel finalize cost what two launches cost), and inside the training step it is slower
+// (ge_bn_fwd_train 4.4 ms vs 2.6 ms per step): a cooperative grid needs every SM at once, so it cannot overlap the
+// graph module's side-stream kernels or the tail of the previous convolution.  Kept for maps-on-chip experiments.
+int g_bn_path = 0;
+
+bool coop_supported() {
+    static int cached = -1;
+    if (cached < 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) v = 0;
+        cached = v ? 1 : 0;
+    }
+    return cached == 1;
+}
+
+template <typename K>
+int coop_launch(K kernel, int grid, size_t smem, void** args, cudaStream_t st, size_t* attr_cache, const char* name) {
+    if (smem > *attr_cache) {
+        GE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+        *attr_cache = smem;
+    }
+    GE_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(ge_bn_coop::CT), args, smem, st), name);
+    ge_count_launches(1);
+    return GE_OK;
+}
+
+// workspace rows: enough for the streaming path's chunks and for one partial per SM of the cooperative path
+size_t bn_ws_rows(long long P, int C) {
+    const size_t a = (size_t)bn_chunks(P, C), b = (size_t)ge::sm_count();
+    return a > b ? a : b;
+}
+
 }  // namespace
 
-// partials [chunks][2][C] followed by the backward's per-segment sums [2][2][C]
+extern "C" int ge_bn_set_path(int path) {
+    GE_REQUIRE(path >= 0 && path <= 2, GE_ERR_ARG, "ge_bn_set_path: path must be 0/1 (streaming kernels) or 2 (cooperative where it fits)");
+    g_bn_path = path;
+    return GE_OK;
+}
+
+// partials [rows][2][C] followed by the backward's per-segment sums [2][2][C]
 extern "C" size_t ge_bn_workspace_bytes(long long P, int C) {
     if (P <= 0 || C <= 0 || !bn_shape_ok(C)) return 0;
-    return ((size_t)bn_chunks(P, C) * 2 * C + 4 * (size_t)C) * sizeof(float);
+    return (bn_ws_rows(P, C) * 2 * C + 4 * (size_t)C) * sizeof(float);
 }
 
 extern "C" size_t ge_bn_relu_mask_bytes(long long P, int C) {
@@ -431,6 +468,26 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
     GE_REQUIRE(bn_shape_ok(C), GE_ERR_SHAPE, "ge_bn_fwd_train: unsupported channel count C=%d (C%%8==0, C/8 | 256)", C);
     GE_REQUIRE(workspace_bytes >= ge_bn_workspace_bytes(P, C), GE_ERR_ARG, "ge_bn_fwd_train: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_fwd_train: unsupported dtype %d", dtype);
+    {   // single-launch path: the map fits the chip's shared memory
+        const int es = dtype == GE_DTYPE_F32 ? 4 : 2;
+        ge_bn_coop::Plan cp;
+        // (not with a residual: its read in the apply phase has too little memory-level parallelism at one CTA per SM;
+        //  measured 50 vs 34 us at [256,1024,7,7])
+        if (g_bn_path == 2 && residual == nullptr && coop_supported() &&
+            ge_bn_coop::coop_fit(P, P_split, C, es, ge::sm_count(), &cp) >= 1) {
+            float* partc = static_cast<float*>(workspace);
+            unsigned short* mkc = relu ? static_cast<unsigned short*>(relu_mask) : nullptr;
+            const size_t smemc = (size_t)cp.max_pixels() * C * es + ge_bn_coop::red_bytes(C, es);
+            void* args[] = {(void*)&x, (void*)&residual, (void*)&gamma, (void*)&beta, (void*)&running_mean, (void*)&running_var,
+                            (void*)&num_batches_tracked, (void*)&momentum, (void*)&eps, (void*)&out, (void*)&save_mean,
+                            (void*)&save_rstd, (void*)&mkc, (void*)&partc, (void*)&cp, (void*)&C, (void*)&relu};
+            static size_t a0 = 0, a1 = 0;
+            if (dtype == GE_DTYPE_F32)
+                return coop_launch(ge_bn_coop::bn_fwd_coop_kernel<float>, cp.G, smemc, args, st, &a0, "ge_bn_fwd_train(coop)");
+            return coop_launch(ge_bn_coop::bn_fwd_coop_kernel<bf16>, cp.G, smemc, args, st, &a1, "ge_bn_fwd_train(coop)");
+        }
+    }
     const SegPlan sp = bn_plan(P, P_split, C);
     const size_t smem = bn_smem(C);
     float* part = static_cast<float*>(workspace);
@@ -446,7 +503,7 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
         bn_partial_stats_kernel<bf16><<<sp.chunks, BN_THREADS, smem, st>>>((const bf16*)x, shift, part, sp, C);
     } else { ge_set_error("ge_bn_fwd_train: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_bn_fwd_train(stats)");
-    bn_finalize_stats_kernel<<<ge::cdiv(C, 32), 32 * FL, 0, st>>>(part, sp, shift, save_mean, save_rstd,
+    bn_finalize_stats_kernel<<<ge::cdiv(C, FCH), FCH * FLN, 0, st>>>(part, sp, shift, save_mean, save_rstd,
                                                                running_mean, running_var, num_batches_tracked, C, eps, momentum);
     GE_CHECK_LAUNCH("ge_bn_fwd_train(finalize)");
     const unsigned blocks4 = (unsigned)ge::cdivll(ge::cdivll(P, FPIX4) * (C / 4), 256);
@@ -494,11 +551,27 @@ extern "C" int ge_bn_bwd(const void* dy, const void* relu_mask, const void* x, c
     GE_REQUIRE(workspace_bytes >= ge_bn_workspace_bytes(P, C), GE_ERR_ARG, "ge_bn_bwd: workspace too small");
     GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_bwd: unsupported dtype %d", dtype);
     cudaStream_t st = (cudaStream_t)stream;
+    float* part = static_cast<float*>(workspace);
+    float* seg_sums = part + bn_ws_rows(P, C) * 2 * C;
+    const unsigned short* mk = relu ? static_cast<const unsigned short*>(relu_mask) : nullptr;
+    {   // single-launch path
+        const int es = dtype == GE_DTYPE_F32 ? 4 : 2;
+        ge_bn_coop::Plan cp;
+        const int fit = (g_bn_path == 2 && coop_supported()) ? ge_bn_coop::coop_fit(P, P_split, C, es, ge::sm_count(), &cp) : 0;
+        if (fit >= 1) {
+            const size_t smemc = (size_t)cp.max_pixels() * C * es * (fit == 2 ? 2 : 1) + ge_bn_coop::red_bytes(C, es);
+            void* args[] = {(void*)&dy, (void*)&mk, (void*)&x, (void*)&gamma, (void*)&mean, (void*)&rstd, (void*)&dx, (void*)&dres,
+                            (void*)&dgamma, (void*)&dbeta, (void*)&part, (void*)&seg_sums, (void*)&cp, (void*)&C};
+            static size_t a[4] = {0, 0, 0, 0};
+            if (dtype == GE_DTYPE_F32)
+                return fit == 2 ? coop_launch(ge_bn_coop::bn_bwd_coop_kernel<float, true>, cp.G, smemc, args, st, &a[0], "ge_bn_bwd(coop)")
+                                : coop_launch(ge_bn_coop::bn_bwd_coop_kernel<float, false>, cp.G, smemc, args, st, &a[1], "ge_bn_bwd(coop)");
+            return fit == 2 ? coop_launch(ge_bn_coop::bn_bwd_coop_kernel<bf16, true>, cp.G, smemc, args, st, &a[2], "ge_bn_bwd(coop)")
+                            : coop_launch(ge_bn_coop::bn_bwd_coop_kernel<bf16, false>, cp.G, smemc, args, st, &a[3], "ge_bn_bwd(coop)");
+        }
+    }
     const SegPlan sp = bn_plan(P, P_split, C);
     const size_t smem = bn_smem(C);
-    float* part = static_cast<float*>(workspace);
-    float* seg_sums = part + (size_t)sp.chunks * 2 * C;
-    const unsigned short* mk = relu ? static_cast<const unsigned short*>(relu_mask) : nullptr;
     static size_t c0 = 0, c1 = 0;
     if (dtype == GE_DTYPE_F32) {
         if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(bn_partial_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_bwd(attr)"); c0 = smem; }
@@ -512,7 +585,7 @@ extern "C" int ge_bn_bwd(const void* dy, const void* relu_mask, const void* x, c
         bn_partial_bwd_kernel<bf16><<<sp.chunks, BN_THREADS, smem, st>>>((const bf16*)dy, mk, (const bf16*)x,
                                                                          mean, rstd, part, sp, C);
     GE_CHECK_LAUNCH("ge_bn_bwd(partial)");
-    bn_finalize_bwd_kernel<<<ge::cdiv(C, 32), 32 * FL, 0, st>>>(part, sp, seg_sums, dgamma, dbeta, C);
+    bn_finalize_bwd_kernel<<<ge::cdiv(C, FCH), FCH * FLN, 0, st>>>(part, sp, seg_sums, dgamma, dbeta, C);
     GE_CHECK_LAUNCH("ge_bn_bwd(finalize)");
     const long long total4 = ge::cdivll(P, BPIX4) * (C / 4);
     const unsigned blocks4 = (unsigned)ge::cdivll(total4, 256);

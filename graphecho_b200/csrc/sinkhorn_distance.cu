@@ -342,7 +342,7 @@ extern "C" int ge_sinkhorn_distance_bwd(const float* x, const float* y, const fl
                                         float* dC, float* dx, float* dy,
                                         int B, int P1, int P2, int D, float eps, int max_iter,
                                         ge_stream_t stream) {
-    GE_REQUIRE(x && y && C && hist_u && hist_v && nits && gcost && dC && dx && dy, GE_ERR_ARG,
+    GE_REQUIRE(x && y && C && hist_u && hist_v && nits && gcost && dC && ((dx && dy) || (!dx && !dy)), GE_ERR_ARG,
                "ge_sinkhorn_distance_bwd: null pointer");
     GE_REQUIRE(B > 0 && P1 > 0 && P2 > 0 && D > 0 && max_iter >= 0 && eps > 0.f, GE_ERR_ARG,
                "ge_sinkhorn_distance_bwd: bad dimension");
@@ -354,6 +354,7 @@ extern "C" int ge_sinkhorn_distance_bwd(const float* x, const float* y, const fl
     { static size_t ge_max_smem__ = 0; if ((size_t)(smem) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(sd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)), "ge_sinkhorn_distance_bwd(attr)"); ge_max_smem__ = (size_t)(smem); } }
     sd_bwd_kernel<<<B, SD_THREADS, smem, st>>>(C, hist_u, hist_v, nits, gcost, dC, P1, P2, eps, max_iter, spill);
     GE_CHECK_LAUNCH("ge_sinkhorn_distance_bwd(sweep)");
+    if (dx == nullptr) return GE_OK;      // the caller turns dC into dx, dy itself (two GEMMs for large node sets)
     const int spill2 = (size_t)P1 * P2 * sizeof(float) > kCap;
     const size_t smem2 = spill2 ? 0 : (size_t)P1 * P2 * sizeof(float);
     { static size_t ge_max_smem__ = 0; if ((size_t)(smem2) > ge_max_smem__) { GE_CUDA(cudaFuncSetAttribute(sd_bwd_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem2)), "ge_sinkhorn_distance_bwd(attr2)"); ge_max_smem__ = (size_t)(smem2); } }

@@ -342,6 +342,9 @@ class UDAEngine:
         return torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.cfg.bf16, cache_enabled=not self.graphed)
 
     def seg_loss(self, logits, masks):
+        """DiceLoss + BCEWithLogitsLoss (train_cardiac_uda.py:228) as one fused pass (csrc/seg_loss.cu)."""
+        if logits.is_cuda and logits.shape[1] <= 8:
+            return GF.seg_loss(logits, masks)
         return self.dice(logits, masks) + F.binary_cross_entropy_with_logits(logits, masks)
 
     def _prepare(self, frames_src, frames_tgt):
@@ -370,10 +373,12 @@ class UDAEngine:
         cfg = self.cfg
         frames_temp, masks_temp, (b, t) = temporal
         nst = masks_temp.shape[0]
+        # the network's own methods, not the _Trunk/_Head wrappers: make_graphed_callables swaps THEIR forward for the
+        # graph replay of the single-frame batch
         with self._autocast():
-            feats = list(self._trunk_raw(frames_temp))
+            feats = list(self.network.forward_trunk(frames_temp))
             with torch.no_grad():
-                logits = self._head_raw(*[f.detach() for f in feats])
+                logits = self.network.forward_head(*[f.detach() for f in feats])
         pred_src = logits[:nst]
         avail = (masks_temp.sum(dim=(1, 2, 3)) > 100).view(-1, 1, 1, 1)                 # :277, 283-290
         targets = torch.where(avail, masks_temp, pred_src.to(masks_temp.dtype))
@@ -405,7 +410,7 @@ class UDAEngine:
             return losses
         if p2g is not None:
             feats = [p2g] + list(feats[1:])
-        score_maps = torch.where(torch.sigmoid(pred_t) > 0.5, 1, 0)                # train_cardiac_uda.py:235
+        score_maps = GF.LogitMap(pred_t.detach())                                  # train_cardiac_uda.py:235, never materialised
         # The graph-matching module is host-driven (two count read-backs, hundreds of tiny launches) while
         # the discriminators are four long GPU-bound graph replays with no dependency on it: run GModule on
         # a side stream so its host synchronisations wait only for its own small kernels and its launch
@@ -482,7 +487,7 @@ class UDAEngine:
         pred_s, pred_t = logits[:ns], logits[ns:]
         seg = cfg.seg_weight * self.seg_loss(pred_s, masks_src)
         losses["seg_loss"] = seg
-        score_maps = torch.where(torch.sigmoid(pred_t) > 0.5, 1, 0)                # train_cardiac_uda.py:235
+        score_maps = GF.LogitMap(pred_t.detach())                                  # train_cardiac_uda.py:235, never materialised
         if side is not None:
             side.wait_stream(main)          # the side stream waits for the pyramid only, NOT for the work issued below
         # 2. discriminators on their own leaves, forward + backward back to back; then the head's backward

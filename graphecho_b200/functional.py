@@ -156,10 +156,14 @@ class _SinkhornDistance(Function):
         P2 = y3.shape[1]
         g = _f32c(gcost)
         dC = torch.empty_like(C)
-        dx, dy = torch.empty_like(x3), torch.empty_like(y3)
+        gemm = P1 * P2 > 128 * 128          # large node sets: dC -> (dx, dy) is two GEMMs, not a one-CTA loop
+        dx, dy = (None, None) if gemm else (torch.empty_like(x3), torch.empty_like(y3))
         call("ge_sinkhorn_distance_bwd", ptr(x3), ptr(y3), ptr(C), ptr(hist_u), ptr(hist_v), ptr(nits),
              ptr(g), ptr(dC), ptr(dx), ptr(dy), B, P1, P2, D, c_float(eps), max_iter, stream(),
              work=(8 * B * D * (P1 + P2) + 8 * B * P1 * P2, 4 * B * P1 * P2 * D + 20 * B * P1 * P2 * max_iter))
+        if gemm:                            # C_ij = sum_d (x_id - y_jd)^2
+            dx = 2.0 * (dC.sum(2, keepdim=True) * x3 - torch.bmm(dC, y3))
+            dy = 2.0 * (dC.sum(1).unsqueeze(2) * y3 - torch.bmm(dC.transpose(1, 2), x3))
         return dx, dy, None, None, None
 
 
@@ -663,6 +667,74 @@ class _SegTail(Function):
 def seg_tail(s2, s3, s4, s5, W3, b3, scale=4):
     """_upsample(conv3(s2+s3+s4+s5), 4h, 4w) -> fp32 NCHW logits (fpnseg.py:444)."""
     return _SegTail.apply(s2, s3, s4, s5, W3, b3, int(scale))
+
+
+# ------------------------------------------------------------------------------------------ f4: losses, score-map boxes
+class _SegLoss(Function):
+    @staticmethod
+    def forward(ctx, logits, target, smooth):
+        _need_cuda(logits, target)
+        x, t = _f32c(logits), _f32c(target)
+        if x.shape != t.shape or x.dim() != 4:
+            raise _cabi.GraphEchoNativeError(f"seg_loss: logits {tuple(x.shape)} and masks {tuple(t.shape)} must be equal [F,nc,H,W]")
+        Fr, nc, H, W = x.shape
+        nbytes = _cabi.lib().ge_seg_loss_workspace_bytes(Fr, nc, H * W)
+        if nbytes == 0:
+            raise _cabi.GraphEchoNativeError(f"seg_loss supports 1..8 classes, got {nc}")
+        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        numden = torch.empty((Fr, nc, 2), device=x.device, dtype=torch.float32)
+        loss = torch.empty(3, device=x.device, dtype=torch.float32)
+        call("ge_seg_loss_fwd", ptr(x), ptr(t), ptr(numden), ptr(loss), ptr(ws), c_size_t(nbytes), Fr, nc, H * W,
+             c_float(smooth), stream(), work=(8 * x.numel(), 30 * x.numel()))
+        ctx.save_for_backward(x, t, numden)
+        return loss[0]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, t, numden = ctx.saved_tensors
+        Fr, nc, H, W = x.shape
+        gout = _f32c(g).reshape(1)
+        dx = torch.empty_like(x)
+        call("ge_seg_loss_bwd", ptr(x), ptr(t), ptr(numden), ptr(gout), ptr(dx), Fr, nc, H * W, stream(),
+             work=(12 * x.numel(), 40 * x.numel()))
+        return dx, None, None
+
+
+def seg_loss(logits, masks, smooth=1.0):
+    """DiceLoss()(logits, masks) + BCEWithLogitsLoss()(logits, masks) (utils/losses.py:64-95 + nn.BCEWithLogitsLoss;
+    train_cardiac_uda.py:228): one fused pass forward, one backward.  logits, masks [F,nc,H,W], nc <= 8."""
+    return _SegLoss.apply(logits, masks, float(smooth))
+
+
+class LogitMap:
+    """A score map given by its logits: `where(sigmoid(logits) > 0.5, 1, 0)` (train_cardiac_uda.py:235) WITHOUT being
+    materialised; the graph module only ever takes its bounding boxes (mask_boxes, mode 1)."""
+
+    def __init__(self, logits):
+        self.logits = logits
+
+    def materialise(self):
+        return torch.where(torch.sigmoid(self.logits) > 0.5, 1, 0)
+
+
+@torch.no_grad()
+def mask_boxes(maps):
+    """[B,K,H,W] masks / score maps (or a LogitMap) -> fp32 [B,K,4] boxes (xmin,ymin,xmax,ymax) of the non-zero pixels,
+    (0,0,W,H) for an empty plane (graph_matching.py:702-746)."""
+    mode = 0
+    if isinstance(maps, LogitMap):
+        maps, mode = maps.logits, 1
+    _need_cuda(maps)
+    if maps.dtype == torch.int64:
+        m, code = maps.contiguous(), 2
+    else:
+        m, code = _f32c(maps), F32
+    B, K, H, W = m.shape
+    boxes = torch.empty((B, K, 4), device=m.device, dtype=torch.float32)
+    call("ge_mask_boxes", ptr(m), ptr(boxes), code, B * K, H, W, mode, stream(),
+         work=(m.numel() * m.element_size(), 4 * m.numel()))
+    return boxes
 
 
 class _GradReverse(Function):

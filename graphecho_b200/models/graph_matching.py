@@ -448,7 +448,10 @@ class GModule(nn.Module):
         return torch.where(empty.unsqueeze(-1), full, box)
 
     def find_bbox(self, masks):
-        """[B,K,H,W] -> [B,K,4] (indexable per image like the reference's list)."""
+        """[B,K,H,W] -> [B,K,4] (indexable per image like the reference's list).  CUDA maps (and score maps given by
+        their logits, GF.LogitMap) take the one-CTA-per-plane kernel."""
+        if isinstance(masks, GF.LogitMap) or (torch.is_tensor(masks) and masks.is_cuda and masks.dim() == 4):
+            return GF.mask_boxes(masks)
         return self._boxes(masks)
 
 

@@ -75,13 +75,14 @@ int ge_sinkhorn_rpm_bwd(const float* M, const float* G, const float* hist_r, con
  * with the batch-mean early stop `err < thresh`, pi = exp((-C+u+v)/eps), cost_b = sum pi*C.
  * x [B,P1,D], y [B,P2,D]; outputs C, pi [B,P1,P2], cost [B]; saved for backward:
  * hist_u [B,max_iter,P1], hist_v [B,max_iter,P2], err [B,max_iter], nits [1] (int32, the
- * number of iterations the reference loop would have executed).  One CTA per batch element;
- * GE_ERR_CAPACITY if P1*P2 does not fit shared memory. */
+ * number of iterations the reference loop would have executed).  One CTA per batch element; when the P1 x P2
+ * matrices do not fit its shared memory (node sets of 200-320 rows) they live in their global output arrays. */
 int ge_sinkhorn_distance_fwd(const float* x, const float* y, float* C, float* pi, float* cost,
                              float* hist_u, float* hist_v, float* err, int* nits,
                              int B, int P1, int P2, int D, float eps, int max_iter, double thresh,
                              ge_stream_t stream);
-/* gcost [B] = dLoss/dcost_b; dC [B,P1,P2] scratch/output; dx [B,P1,D], dy [B,P2,D]. */
+/* gcost [B] = dLoss/dcost_b; dC [B,P1,P2] scratch/output; dx [B,P1,D], dy [B,P2,D] -- or both NULL: only dC is
+ * produced and the caller forms dx = 2(rowsum(dC) x - dC y), dy = 2(colsum(dC) y - dC^T x) itself (GEMM-shaped). */
 int ge_sinkhorn_distance_bwd(const float* x, const float* y, const float* C, const float* hist_u,
                              const float* hist_v, const int* nits, const float* gcost,
                              float* dC, float* dx, float* dy,
@@ -196,6 +197,11 @@ int ge_seg_tail_bwd(const float* dlogits, const void* s2, const void* s3, const 
  * the forward and consumed by the backward, which therefore never re-reads `out`. */
 size_t ge_bn_workspace_bytes(long long P, int C);
 size_t ge_bn_relu_mask_bytes(long long P, int C);
+/* 0 / 1 (default): the three-kernel streaming path.  2: maps that fit the chip's shared memory (<= ~28 MB; for the
+ * backward x and dy, or x alone) take a single-launch cooperative kernel -- x read from HBM once, statistics /
+ * finalize / apply separated by grid barriers.  Measured no faster alone and slower inside the training step (a
+ * cooperative grid cannot overlap other streams), hence opt-in. */
+int ge_bn_set_path(int path);
 int ge_bn_fwd_train(const void* x, const void* residual, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, long long* num_batches_tracked,
                     float momentum, float eps, void* out, float* save_mean, float* save_rstd,
@@ -227,6 +233,22 @@ int ge_maxpool3s2_fwd(const void* x, void* out, unsigned char* arg, int dtype,
                       int N, int H, int W, int C, ge_stream_t stream);
 int ge_maxpool3s2_bwd(const void* dout, const unsigned char* arg, void* dx, int dtype,
                       int N, int H, int W, int C, ge_stream_t stream);
+
+/* ---- segmentation loss and score-map boxes (the full-resolution passes around the network) -------
+ * seg_loss = DiceLoss()(pred, masks) + BCEWithLogitsLoss()(pred, masks) (train_cardiac_uda.py:228, train_camus_echo.py:212;
+ * utils/losses.py:64-95: softmax over classes, BinaryDiceLoss(smooth=1, p=2) per class averaged over frames, / nc).
+ * logits, target fp32 NCHW [F,nc,H*W], nc <= 8.  Forward: one pass; numden fp32 [F,nc,2] is saved for the backward;
+ * loss fp32 [3] = (dice + bce, dice, bce).  Backward: one pass, dlogits = gout[0] * d loss[0] / d logits. */
+size_t ge_seg_loss_workspace_bytes(int F, int nc, int HW);
+int ge_seg_loss_fwd(const float* logits, const float* target, float* numden, float* loss, void* workspace,
+                    size_t workspace_bytes, int F, int nc, int HW, float smooth, ge_stream_t stream);
+int ge_seg_loss_bwd(const float* logits, const float* target, const float* numden, const float* gout,
+                    float* dlogits, int F, int nc, int HW, ge_stream_t stream);
+/* GModule.find_bbox / masks_to_boxes (models/graph_matching.py:702-746): boxes fp32 [planes,4] = (xmin,ymin,xmax,ymax)
+ * of the "on" pixels of every [H,W] plane, (0,0,W,H) for an empty plane.  dtype GE_DTYPE_F32 or 2 (int64).
+ * mode 0: on = value != 0; mode 1: on = value > 0 -- the box of `where(sigmoid(pred) > 0.5, 1, 0)`
+ * (train_cardiac_uda.py:235) straight from the logits, without materialising the score map. */
+int ge_mask_boxes(const void* maps, float* boxes, int dtype, int planes, int H, int W, int mode, ge_stream_t stream);
 
 #ifdef __cplusplus
 }

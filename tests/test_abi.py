@@ -74,3 +74,17 @@ def test_new_wrappers_reject_cpu_tensors():
         GF.maxpool3s2(torch.randn(1, 8, 6, 6))
     with pytest.raises(RuntimeError, match="CUDA"):
         GF.gn_relu(torch.randn(1, 32, 4, 4), torch.ones(32), torch.zeros(32), 4, pre_bias=torch.zeros(32))
+
+
+def test_round2_entry_points_validate_arguments_without_a_gpu():
+    lib = _cabi.lib()
+    assert lib.ge_bn_set_path(5) < 0 and "path" in _cabi.last_error()
+    assert lib.ge_bn_set_path(0) == 0
+    assert lib.ge_bn_relu_mask_bytes(200704, 256) == 200704 * 256 // 8          # one bit per element
+    assert lib.ge_bn_relu_mask_bytes(10, 12) == 0
+    assert lib.ge_seg_loss_workspace_bytes(4, 9, 100) == 0                     # at most 8 classes
+    assert lib.ge_seg_loss_fwd(None, None, None, None, None, 0, 1, 2, 16, 1.0, None) < 0 and "null" in _cabi.last_error()
+    assert lib.ge_mask_boxes(None, None, 0, 1, 4, 4, 0, None) < 0
+    with pytest.raises(RuntimeError, match="CUDA"):
+        from graphecho_b200 import functional as GF
+        GF.seg_loss(torch.randn(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))

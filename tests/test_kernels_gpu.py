@@ -496,9 +496,13 @@ def test_spectral_bipartition_large_kernel_matches_dense_route(dev):
 @pytest.mark.parametrize("C,hw,res,relu,dtype", [(64, 28, False, True, torch.float32), (256, 14, True, True, torch.float32),
                                                  (2048, 4, True, True, torch.float32), (512, 7, False, False, torch.float32),
                                                  (1024, 7, True, True, torch.bfloat16), (128, 56, False, True, torch.bfloat16)])
-def test_bn_act_train_and_eval(dev, C, hw, res, relu, dtype):
+@pytest.mark.parametrize("bn_path", [0, 2])
+def test_bn_act_train_and_eval(dev, C, hw, res, relu, dtype, bn_path):
     """Fused BN(+residual)(+ReLU) against nn.BatchNorm2d + add + relu (fp32 oracle on CPU): output,
-    grads of x / residual / gamma / beta, running statistics, then inference mode."""
+    grads of x / residual / gamma / beta, running statistics, then inference mode.  bn_path 0 = the three-kernel
+    streaming path (default), 2 = the single-launch cooperative kernels (these maps fit on chip)."""
+    from graphecho_b200 import _cabi
+    _cabi.lib().ge_bn_set_path(bn_path)
     torch.manual_seed(C + hw)
     N = 5
     x = (torch.randn(N, C, hw, hw) * 1.4 + 0.3).to(dtype).float()
@@ -541,6 +545,7 @@ def test_bn_act_train_and_eval(dev, C, hw, res, relu, dtype):
         ref_e = torch.relu(y) if relu else y
         out_e = GF.bn_act(_cl(x, dev, dtype), our_bn, residual=None if not res else _cl(r, dev, dtype), relu=relu)
     close(out_e, ref_e, rtol=2e-2 if lo else 1e-4, atol=3e-2 if lo else 2e-5)
+    _cabi.lib().ge_bn_set_path(0)
 
 
 @pytest.mark.parametrize("C,hw,N,ns,res,relu,dtype", [(64, 7, 5, 3, False, True, torch.float32),     # P_split = 147: a thread straddles
@@ -549,11 +554,14 @@ def test_bn_act_train_and_eval(dev, C, hw, res, relu, dtype):
                                                        (512, 7, 5, 4, False, False, torch.float32),
                                                        (256, 28, 8, 4, True, True, torch.bfloat16),
                                                        (64, 56, 4, 2, False, True, torch.bfloat16)])
-def test_bn_act_domain_split_equals_two_calls(dev, C, hw, N, ns, res, relu, dtype):
+@pytest.mark.parametrize("bn_path", [0, 2])
+def test_bn_act_domain_split_equals_two_calls(dev, C, hw, N, ns, res, relu, dtype, bn_path):
     """Per-domain statistics: one fused call on the [source | target] batch under GF.domain_split(ns) == two separate
     nn.BatchNorm2d calls, source first (train_cardiac_uda.py:225, 234): outputs, all gradients (gamma / beta gradients
     accumulate over the two calls), running statistics after TWO momentum updates, num_batches_tracked == 2."""
     import copy
+    from graphecho_b200 import _cabi
+    _cabi.lib().ge_bn_set_path(bn_path)
     torch.manual_seed(C + hw + ns)
     x = torch.cat([torch.randn(ns, C, hw, hw) * 1.4 + 0.3, torch.randn(N - ns, C, hw, hw) * 0.6 - 0.5]).to(dtype).float()
     r = torch.randn(N, C, hw, hw).to(dtype).float() if res else None
@@ -591,6 +599,7 @@ def test_bn_act_domain_split_equals_two_calls(dev, C, hw, N, ns, res, relu, dtyp
         whole = GF.bn_act(_cl(x, dev, dtype), copy.deepcopy(ref_bn).to(dev).train(), residual=None if not res else _cl(r, dev, dtype),
                           relu=relu)
     assert (whole.float().cpu() - ref).abs().max() > 0.05
+    _cabi.lib().ge_bn_set_path(0)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -637,3 +646,44 @@ def test_maxpool3s2_matches_torch(dev, dtype, hw):
     close(out.float(), ref, rtol=0, atol=0)
     (out.float() * Wt.to(dev)).sum().backward()
     close(xd.grad.float(), xo.grad, rtol=1e-6 if dtype == torch.float32 else 1e-2, atol=1e-6 if dtype == torch.float32 else 2e-2)
+
+
+# ---------------------------------------------------------------------------------------- f4: loss fusion, boxes
+@pytest.mark.parametrize("F_,nc,hw", [(3, 1, 28), (5, 2, 112), (2, 4, 256), (4, 3, 37)])
+def test_seg_loss_fused_vs_oracle(dev, F_, nc, hw):
+    """DiceLoss + BCEWithLogits as one pass (utils/losses.py:64-95 + BCEWithLogitsLoss) against the oracle: value and
+    the gradient w.r.t. the logits."""
+    from oracle import fpn_ops as FP
+    from graphecho_b200 import synth
+    torch.manual_seed(F_ * 10 + nc)
+    x = (torch.randn(F_, nc, hw, hw) * 2.0).requires_grad_()
+    t = synth.disc_masks(F_, nc, hw)
+    ref = FP.seg_loss(x, t)
+    (ref * 1.7).backward()
+    xd = x.detach().to(dev).requires_grad_()
+    out = GF.seg_loss(xd, t.to(dev))
+    (out * 1.7).backward()
+    close(out, ref, rtol=2e-5, atol=1e-6)
+    close(xd.grad, x.grad, rtol=1e-4, atol=1e-9 + 1e-5 * float(x.grad.abs().max()))
+
+
+def test_mask_boxes_vs_oracle(dev):
+    """Bounding boxes of mask / score-map planes (graph_matching.py:702-746): fp32 masks, int64 thresholded score maps,
+    logits taken through sigmoid > 0.5 without materialising the map, an empty plane, a full plane."""
+    from oracle import gmodule_ops as GM
+    from graphecho_b200 import synth
+    masks = synth.disc_masks(5, 4, 256)
+    masks[2, 1] = 0                                          # empty plane -> (0, 0, W, H)
+    masks[3, 2] = 1                                          # full plane
+    ref = torch.stack(GM.find_bbox(masks))
+    assert torch.equal(GF.mask_boxes(masks.to(dev)).cpu(), ref)
+    assert torch.equal(GF.mask_boxes(masks.long().to(dev)).cpu(), ref)
+    torch.manual_seed(0)
+    logits = torch.randn(3, 2, 112, 96) - 1.5
+    logits[1, 0] = -3.0
+    score = torch.where(torch.sigmoid(logits) > 0.5, 1, 0)
+    ref = torch.stack(GM.find_bbox(score))
+    assert torch.equal(GF.mask_boxes(GF.LogitMap(logits.to(dev))).cpu(), ref)
+    assert torch.equal(GF.mask_boxes(score.to(dev)).cpu(), ref)
+    # raw logits used as a score map (the temporal branch, Appendix A-12): every plane is "full"
+    assert torch.equal(GF.mask_boxes(logits.to(dev)).cpu(), torch.stack(GM.find_bbox(logits)))
