@@ -59,6 +59,9 @@ _SIGNATURES = {
     "ge_bn_fwd_train": (c_int, [P, P, P, P, P, P, P, F, F, P, P, P, P, P, Z, I, L, L, I, I, P]),
     "ge_bn_fwd_eval": (c_int, [P, P, P, P, P, P, F, P, I, L, I, I, P]),
     "ge_bn_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, Z, I, L, L, I, I, P]),
+    "ge_tgcn_recurrence_supported": (c_int, [I, I, I, I, I, I]),
+    "ge_tgcn_recurrence_fwd": (c_int, [P, P, P, P, P, P, P, I, I, I, I, I, P]),
+    "ge_tgcn_recurrence_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P]),
     "ge_seg_loss_workspace_bytes": (c_size_t, [I, I, I]),
     "ge_seg_loss_fwd": (c_int, [P, P, P, P, P, Z, I, I, I, F, P]),
     "ge_seg_loss_bwd": (c_int, [P, P, P, P, P, I, I, I, P]),

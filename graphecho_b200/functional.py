@@ -366,6 +366,57 @@ def pool_concat(levels, rs):
     return _PoolConcat.apply(tuple(int(r) for r in rs), *levels)
 
 
+def tgcn_recurrence_supported(C, Cout, N, k, dilation, groups):
+    return bool(_cabi.lib().ge_tgcn_recurrence_supported(int(C), int(Cout), int(N), int(k), int(dilation), int(groups)))
+
+
+class _TgcnRecurrence(Function):
+    @staticmethod
+    def forward(ctx, emb, weight, bias, k):
+        _need_cuda(emb, weight, bias)
+        e = _f32c(emb)
+        B, T, C, N = e.shape
+        W2 = _f32c(weight).reshape(weight.shape[0], -1)                  # [Cout, 2C/groups]
+        Wt = W2.t().contiguous()
+        bz = _f32c(bias)
+        dev = e.device
+        hidden_all = torch.empty((B, T, C, N), device=dev, dtype=torch.float32)
+        z_all = torch.empty_like(hidden_all)
+        idx_all = torch.empty((B, T, N, k), device=dev, dtype=torch.int32)
+        argk_all = torch.empty((B, T, C, N), device=dev, dtype=torch.uint8)
+        call("ge_tgcn_recurrence_fwd", ptr(e), ptr(Wt), ptr(bz), ptr(hidden_all), ptr(z_all), ptr(idx_all), ptr(argk_all),
+             B, T, C, N, int(k), stream(),
+             work=(B * T * C * N * 4 * 3 + Wt.numel() * 4, 2 * B * T * (N * N * C + N * C * W2.shape[1]) + 2 * B * T * C * N * int(k)))
+        ctx.save_for_backward(e, W2, hidden_all, z_all, idx_all, argk_all)
+        ctx.cfg = (int(k), weight.shape, weight.dtype, bias.dtype)
+        ctx.mark_non_differentiable(idx_all)
+        return hidden_all[:, T - 1], idx_all
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dH, _):
+        e, W2, hidden_all, z_all, idx_all, argk_all = ctx.saved_tensors
+        k, wshape, wdt, bdt = ctx.cfg
+        B, T, C, N = e.shape
+        dev = e.device
+        g = _f32c(dH)
+        d_emb = torch.empty_like(e)
+        dWt_part = torch.zeros((B, W2.shape[1], C), device=dev, dtype=torch.float32)
+        db_part = torch.zeros((B, C), device=dev, dtype=torch.float32)
+        scratch = torch.empty((B, C, N), device=dev, dtype=torch.float32)
+        call("ge_tgcn_recurrence_bwd", ptr(e), ptr(W2), ptr(hidden_all), ptr(z_all), ptr(idx_all), ptr(argk_all), ptr(g),
+             ptr(d_emb), ptr(dWt_part), ptr(db_part), ptr(scratch), B, T, C, N, k, stream(),
+             work=(B * T * C * N * 4 * 4, 4 * B * T * N * C * W2.shape[1]))
+        dW = dWt_part.sum(0).t().reshape(wshape).to(wdt)
+        return d_emb, dW, db_part.sum(0).to(bdt), None
+
+
+def tgcn_recurrence(emb, weight, bias, k=9):
+    """The TGCN time loop (TGCN.py:224-235 over :62-78, state-independent part hoisted out) in one persistent launch:
+    emb [B,T,C,N] -> (final hidden state [B,C,N], neighbour lists int32 [B,T,N,k])."""
+    return _TgcnRecurrence.apply(emb, weight, bias, int(k))
+
+
 # ------------------------------------------------------------------------------------------ K7
 class _UpsampleAdd(Function):
     @staticmethod

@@ -174,12 +174,7 @@ class TGCN(nn.Module):
             _, C, H, W = emb.shape
             emb = emb.float().reshape(batch_size, seq_len, C, H, W) + self.pos_embed[:seq_len, 0].unsqueeze(0)
             emb = emb.reshape(batch_size, seq_len, C, H * W)                         # -> [B,C,N] per step
-            hidden = torch.zeros(batch_size, self._input_dim, self.clip_h * self.clip_w,
-                                 device=x_f1.device, dtype=torch.float32)           # TGCN.py:230
-            for i in range(seq_len):
-                x = emb[:, i].contiguous().unsqueeze(-1)
-                hidden = self.grapher.graph_step(x, hidden).reshape(batch_size, -1, H * W)
-            current_graph = hidden
+            current_graph = self._recurrence(emb, H * W)
             output_f = self.prediction(current_graph.reshape(batch_size, -1, H, W)).view(batch_size, -1)
             update_index_source, update_index_target = update_index
 
@@ -210,6 +205,27 @@ class TGCN(nn.Module):
             elif self.transport_method == "sinkhorn_distance":
                 losses["sinkhorn_loss"] = loss_trans(nodes_g[: batch_size // 2], nodes_g[batch_size // 2:])[0]
         return losses
+
+    persistent_recurrence = True          # one launch for the whole time loop where the kernel covers the shape
+
+    def _recurrence(self, emb, N):
+        """hidden_t = DyGraphConv2d.graph_step(x_t, hidden_{t-1}), hidden_0 = 0 (TGCN.py:230-235).  The persistent kernel
+        (ge_tgcn_recurrence_*) runs all steps in one launch; other shapes take the step-by-step path."""
+        B, T, C, _ = emb.shape
+        g = self.grapher
+        seq = getattr(g.gconv, "nn", None)
+        conv = seq[0] if seq is not None and len(seq) == 2 else None
+        if (self.persistent_recurrence and emb.is_cuda and conv is not None and isinstance(seq[1], nn.GELU)
+                and conv.bias is not None and self._input_dim == C
+                and not g.dilated_knn_graph._dilated.stochastic
+                and GF.tgcn_recurrence_supported(C, conv.out_channels, N, g.k, g.d, conv.groups)):
+            hidden, _ = GF.tgcn_recurrence(emb.contiguous(), conv.weight, conv.bias, g.k)
+            return hidden
+        hidden = torch.zeros(B, self._input_dim, self.clip_h * self.clip_w, device=emb.device, dtype=torch.float32)
+        for i in range(T):
+            x = emb[:, i].contiguous().unsqueeze(-1)
+            hidden = g.graph_step(x, hidden).reshape(B, -1, N)
+        return hidden
 
     @torch.no_grad()
     def _momentum_update_key_encoder(self, encoder_q, encoder_k):

@@ -376,26 +376,40 @@ class GModule(nn.Module):
         nodes = nodes.detach()
         if layout is None:
             layout = [(cls, None) for cls in labels.unique().long().tolist()]
-        off = 0
-        for cls, count in layout:
+        # the classes are independent (each writes its own bank row) and the device bipartition is one latency-bound
+        # CTA per class (~1 ms): fan the classes out over a few streams so they run side by side
+        outer = torch.cuda.current_stream() if nodes.is_cuda else None
+        fan = outer is not None and self.cluster_backend == "device" and len(layout) > 1
+        if fan and len(getattr(self, "_bank_streams", [])) < len(layout):
+            self._bank_streams = [torch.cuda.Stream(device=nodes.device) for _ in range(len(layout))]
+        off, used = 0, []
+        for n_cls, (cls, count) in enumerate(layout):
             if count is None:
                 bs = nodes[labels == cls]
             else:
                 bs = nodes[off:off + count]       # regrouped class-major: a contiguous slice, no sync
                 off += count
-            if len(bs) > k and self.with_cluster_update:
-                keep = self._bipartition(torch.cat([bank[cls][None, :], bs]))
-                # mean of the kept rows without a boolean gather (bs[keep] would synchronise the host with the
-                # clustering kernel).  If the seed ends up alone in its cluster (possible while the bank is still
-                # far from the features) the reference takes the mean of nothing = NaN and poisons the bank for the
-                # rest of training; here such a step falls back to the plain class mean instead.
-                w = keep.to(bs.dtype)
-                cnt = w.sum()
-                bs = torch.where(cnt > 0, (bs * w[:, None]).sum(0) / cnt.clamp_min(1.0), bs.mean(0))
-            else:
-                bs = bs.mean(0)
-            mom = F.cosine_similarity(bs.unsqueeze(0), bank[cls].unsqueeze(0))
-            bank[cls] = bank[cls] * mom + bs * (1.0 - mom)
+            st = None
+            if fan and len(bs) > k and self.with_cluster_update:
+                st = self._bank_streams[n_cls]
+                st.wait_stream(outer)
+                used.append(st)
+            with torch.cuda.stream(st) if st is not None else _null_ctx():
+                if len(bs) > k and self.with_cluster_update:
+                    keep = self._bipartition(torch.cat([bank[cls][None, :], bs]))
+                    # mean of the kept rows without a boolean gather (bs[keep] would synchronise the host with the
+                    # clustering kernel).  If the seed ends up alone in its cluster (possible while the bank is still
+                    # far from the features) the reference takes the mean of nothing = NaN and poisons the bank for the
+                    # rest of training; here such a step falls back to the plain class mean instead.
+                    w = keep.to(bs.dtype)
+                    cnt = w.sum()
+                    bs = torch.where(cnt > 0, (bs * w[:, None]).sum(0) / cnt.clamp_min(1.0), bs.mean(0))
+                else:
+                    bs = bs.mean(0)
+                mom = F.cosine_similarity(bs.unsqueeze(0), bank[cls].unsqueeze(0))
+                bank[cls] = bank[cls] * mom + bs * (1.0 - mom)
+        for st in used:
+            outer.wait_stream(st)
 
     def _bipartition(self, pts):
         """Boolean mask over pts[1:]: the points that fall in the same spectral cluster as pts[0]."""

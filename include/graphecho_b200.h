@@ -234,6 +234,25 @@ int ge_maxpool3s2_fwd(const void* x, void* out, unsigned char* arg, int dtype,
 int ge_maxpool3s2_bwd(const void* dout, const unsigned char* arg, void* dx, int dtype,
                       int N, int H, int W, int C, ge_stream_t stream);
 
+/* ---- K6: the TGCN recurrence as one persistent launch ---------------------------------------------
+ * TGCN.forward's time loop (models/TGCN.py:224-235) over DyGraphConv2d.forward (:62-78) AFTER the state-independent
+ * part (pooling, MLP, position embedding) has been hoisted out: per step
+ *   hidden_t = GELU(Conv1x1_{groups=4}(interleave[x_t ; max_k(hidden_{t-1}[:, nn_k] - x_t)]) + bias),
+ * nn_k = the k nearest hidden_{t-1} nodes of every x_t node on channel-normalised vectors (vig.py:369-381), hidden_0 = 0.
+ * One CTA per clip keeps hidden / x_t / the max-relative features in shared memory for all T steps.
+ * emb fp32 [B,T,C,N]; Wt fp32 [2C/4, C] = TRANSPOSED conv weight; W fp32 [C, 2C/4]; bias fp32 [C].
+ * hidden_all, z_all fp32 [B,T,C,N] (hidden_all[:,T-1] = result; z = pre-activation), idx_all int32 [B,T,N,k],
+ * argk_all uint8 [B,T,C,N] are written by the forward and read by the backward.  Backward: dH fp32 [B,C,N] ->
+ * d_emb fp32 [B,T,C,N], dWt_part fp32 [B,2C/4,C] and db_part fp32 [B,C] (ZERO-FILLED by the caller, summed over B by the
+ * caller), scratch fp32 [B,C,N].  Supported: C = 256, N = 64, k <= 16, dilation 1, groups 4 (ge_tgcn_recurrence_supported). */
+int ge_tgcn_recurrence_supported(int C, int Cout, int N, int k, int dilation, int groups);
+int ge_tgcn_recurrence_fwd(const float* emb, const float* Wt, const float* bias, float* hidden_all, float* z_all,
+                           int* idx_all, unsigned char* argk_all, int B, int T, int C, int N, int k, ge_stream_t stream);
+int ge_tgcn_recurrence_bwd(const float* emb, const float* W, const float* hidden_all, const float* z_all,
+                           const int* idx_all, const unsigned char* argk_all, const float* dH, float* d_emb,
+                           float* dWt_part, float* db_part, float* scratch, int B, int T, int C, int N, int k,
+                           ge_stream_t stream);
+
 /* ---- segmentation loss and score-map boxes (the full-resolution passes around the network) -------
  * seg_loss = DiceLoss()(pred, masks) + BCEWithLogitsLoss()(pred, masks) (train_cardiac_uda.py:228, train_camus_echo.py:212;
  * utils/losses.py:64-95: softmax over classes, BinaryDiceLoss(smooth=1, p=2) per class averaged over frames, / nc).

@@ -335,10 +335,14 @@ def test_gmodule_no_nodes_early_return(dev):
     assert losses == {} and n1.shape[0] == 0
 
 
+@pytest.mark.parametrize("persistent", [True, False])
 @pytest.mark.parametrize("transport", ["node_discriminate", "sinkhorn_distance"])
-def test_tgcn(dev, golden, transport):
+def test_tgcn(dev, golden, transport, persistent):
+    """TGCN.forward against the reference fixture, through the persistent recurrence kernel (one launch for the time
+    loop, ge_tgcn_recurrence_fwd/bwd) and through the step-by-step path."""
     rec = golden("tgcn")[transport]
     m = no_dropout(fill_module(quiet(tgcn_mod.TGCN, 256, 256, (3, 8, 8), 10, 10, None, transport))).to(dev).train()
+    m.persistent_recurrence = persistent
     feats = [f.to(dev).requires_grad_() for f in synth.clip_pyramid(2, 3, 256, seed=31)]
     idx = (torch.zeros(1, dtype=torch.long, device=dev), torch.zeros(1, dtype=torch.long, device=dev))
     losses = m(feats, (rec["src"].to(dev), rec["tgt"].to(dev)), SinkhornDistance(0.1, 5, "mean"),
@@ -355,6 +359,47 @@ def test_tgcn(dev, golden, transport):
     relclose(m.pos_embed.grad[:, :, :8], rec["dpos"], tol)
     close(m.grapher.MLP[1].running_mean, rec["mlp_rm"], rtol=1e-4, atol=1e-6)
     close(m.prediction[1].running_var, rec["pred_rv"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("T,tol", [(2, 2e-4), (6, 5e-2)])
+def test_tgcn_persistent_recurrence_equals_the_step_by_step_path(dev, T, tol):
+    """The one-launch recurrence (hidden / x_t / max-relative features resident in shared memory for all T steps) against
+    the per-step k-NN + gather + grouped conv + GELU path and against the oracle: final hidden state, the neighbour lists
+    of every step, and the gradients w.r.t. the embedded frames, the conv weight and its bias.  B = 5 clips.
+    T = 2 (step 0 is the all-ties step, one real k-NN step): exact to fp32 round-off.  T = 6: a near-tie resolved the
+    other way re-routes one node's neighbours and the difference is carried through the remaining steps, so the two
+    paths are compared at 5e-2 (relative Frobenius; measured 2.6e-2) and the neighbour lists against the oracle's with a near-tie budget."""
+    from graphecho_b200 import functional as GF
+    from oracle import vig_ops as V
+    torch.manual_seed(7)
+    B, C, N = 5, 256, 64
+    m = fill_module(quiet(tgcn_mod.TGCN, 256, 256, (T, 8, 8), 10, 10)).to(dev).train()
+    conv = m.grapher.gconv.nn[0]
+    emb = (torch.randn(B, T, C, N) * 0.7)
+    G = torch.randn(B, C, N)
+    res = []
+    for persistent in (True, False):
+        m.persistent_recurrence = persistent
+        m.zero_grad()
+        e = emb.to(dev).requires_grad_()
+        h = m._recurrence(e, N)
+        (h * G.to(dev)).sum().backward()
+        res.append((h.detach().cpu(), e.grad.cpu(), conv.weight.grad.cpu().clone(), conv.bias.grad.cpu().clone()))
+    for a, b in zip(*res):
+        relclose(a, b, tol)
+    # oracle: hidden state and neighbour lists step by step (TGCN.py:62-78 from the embedded frames on)
+    P = {"grapher.gconv.nn.0.weight": conv.weight.detach().cpu(), "grapher.gconv.nn.0.bias": conv.bias.detach().cpu()}
+    hid = torch.zeros(B, C, N)
+    _, idx_all = GF.tgcn_recurrence(emb.to(dev), conv.weight, conv.bias, 9)
+    flips = 0
+    for t in range(T):
+        x = emb[:, t].reshape(B, C, N, 1)
+        edge = V.dense_dilated_knn(x, hid, 9, 1)
+        if t > 0:                                   # step 0: hidden = 0, every distance ties (Appendix A / TGCN.py:230)
+            flips += int((edge[0] != idx_all[:, t].cpu().long()).sum())
+        hid = V.mrconv(x, edge, P, "grapher.gconv.nn.", y=hid, norm=None, act="gelu").reshape(B, C, N)
+    assert flips <= max(2, 0.004 * B * (T - 1) * N * 9), flips          # near-ties only
+    relclose(res[0][0], hid, 10 * tol)
 
 
 def test_tgcn_rejects_112_inputs_like_the_reference(dev):
