@@ -57,6 +57,10 @@ _SIGNATURES = {
     "ge_bn_relu_mask_bytes": (c_size_t, [L, I]),
     "ge_bn_set_path": (c_int, [I]),
     "ge_bn_fwd_train": (c_int, [P, P, P, P, P, P, P, F, F, P, P, P, P, P, Z, I, L, L, I, I, P]),
+    "ge_bn_fwd_train_prestat": (c_int, [P, P, P, P, P, P, P, F, F, P, P, P, P, P, I, I, I, L, L, I, I, P]),
+    "ge_conv1x1_tc_supported": (c_int, [L, I, I]),
+    "ge_conv1x1_tc_partial_rows": (c_int, [L, L, I, I, P]),
+    "ge_conv1x1_bn_stats": (c_int, [P, P, P, P, P, L, L, I, I, P]),
     "ge_bn_fwd_eval": (c_int, [P, P, P, P, P, P, F, P, I, L, I, I, P]),
     "ge_bn_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, Z, I, L, L, I, I, P]),
     "ge_tgcn_recurrence_supported": (c_int, [I, I, I, I, I, I]),

@@ -518,6 +518,44 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
     return GE_OK;
 }
 
+// Training-mode forward for an x whose per-CTA partial statistics already exist (written by the epilogue of
+// ge_conv1x1_bn_stats, which produced x): finalize + apply only -- the statistics pass over x is gone.
+// part fp32 [rows][2][C]: sums of (x - shift) and (x - shift)^2 with shift = running_mean as it is BEFORE this call
+// (zero when running_mean is NULL); rows [0, rows_segment0) cover pixels [0, P_split), the rest [P_split, P).
+extern "C" int ge_bn_fwd_train_prestat(const void* x, const void* residual, const float* gamma, const float* beta,
+                                       float* running_mean, float* running_var, long long* num_batches_tracked,
+                                       float momentum, float eps, void* out, float* save_mean, float* save_rstd,
+                                       void* relu_mask, const float* part, int rows, int rows_segment0,
+                                       int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream) {
+    GE_REQUIRE(x && gamma && beta && out && save_mean && save_rstd && part, GE_ERR_ARG, "ge_bn_fwd_train_prestat: null pointer");
+    GE_REQUIRE(P > 0 && C > 0 && P_split >= 0 && P_split <= P && rows > 0, GE_ERR_ARG, "ge_bn_fwd_train_prestat: bad dimension");
+    GE_REQUIRE(C % 8 == 0, GE_ERR_SHAPE, "ge_bn_fwd_train_prestat: C=%d must be a multiple of 8", C);
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_fwd_train_prestat: unsupported dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    SegPlan sp;
+    sp.P = P;
+    sp.P0 = (P_split > 0 && P_split < P) ? P_split : P;
+    sp.chunks = rows;
+    sp.chunks0 = sp.P0 < P ? rows_segment0 : rows;
+    sp.ppc0 = sp.ppc1 = 0;
+    GE_REQUIRE(sp.chunks0 >= 1 && (sp.P0 == P || sp.chunks0 < rows), GE_ERR_ARG, "ge_bn_fwd_train_prestat: bad segment rows");
+    const float* shift = running_mean != nullptr ? running_mean : save_mean;
+    if (running_mean == nullptr) GE_CUDA(cudaMemsetAsync(save_mean, 0, (size_t)C * sizeof(float), st), "ge_bn_fwd_train_prestat(memset)");
+    bn_finalize_stats_kernel<<<ge::cdiv(C, FCH), FCH * FLN, 0, st>>>(part, sp, shift, save_mean, save_rstd,
+                                                               running_mean, running_var, num_batches_tracked, C, eps, momentum);
+    GE_CHECK_LAUNCH("ge_bn_fwd_train_prestat(finalize)");
+    const unsigned blocks4 = (unsigned)ge::cdivll(ge::cdivll(P, FPIX4) * (C / 4), 256);
+    unsigned short* mk = relu ? static_cast<unsigned short*>(relu_mask) : nullptr;
+    if (dtype == GE_DTYPE_F32)
+        bn_apply_fwd4_kernel<float, 0><<<blocks4, 256, 0, st>>>((const float*)x, (const float*)residual, save_mean, save_rstd,
+                                                                 gamma, beta, (float*)out, mk, P, sp.P0, C, eps, relu);
+    else
+        bn_apply_fwd4_kernel<bf16, 0><<<blocks4, 256, 0, st>>>((const bf16*)x, (const bf16*)residual, save_mean, save_rstd,
+                                                                gamma, beta, (bf16*)out, mk, P, sp.P0, C, eps, relu);
+    GE_CHECK_LAUNCH("ge_bn_fwd_train_prestat(apply)");
+    return GE_OK;
+}
+
 extern "C" int ge_bn_fwd_eval(const void* x, const void* residual, const float* gamma, const float* beta,
                               const float* running_mean, const float* running_var, float eps, void* out,
                               int dtype, long long P, int C, int relu, ge_stream_t stream) {

@@ -11,7 +11,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _cabi
 from ._cabi import call, ptr, stream
-from ctypes import c_int, c_float, c_double, c_size_t, c_longlong
+from ctypes import c_int, c_float, c_double, c_size_t, c_longlong, byref as ctypes_byref
 
 F32, BF16 = 0, 1
 
@@ -677,6 +677,106 @@ def bn_act(x, bn, residual=None, relu=True):
          ptr(bn.running_var), c_float(bn.eps), ptr(out), _dtype_code(xc), c_longlong(N * H * W), C, int(relu), stream(),
          work=(N * H * W * C * es * (2 + (1 if rc is not None else 0)), 4 * N * H * W * C))
     return out
+
+
+# ------------------------------------------------------------------------------------------ f3: 1x1 conv GEMM + BN statistics
+def conv1x1_tc_supported(P, K, N):
+    return bool(_cabi.lib().ge_conv1x1_tc_supported(c_longlong(int(P)), int(K), int(N)))
+
+
+def conv1x1_gemm(x2d, w2d, shift=None, want_stats=False, P_split=0):
+    """y [P,N] = x2d [P,K] @ w2d [N,K]^T on the tcgen05 kernel (bf16 in / out, fp32 accumulate).  With want_stats also
+    returns the per-CTA partial rows [rows,2,N] of sum(y - shift), sum((y - shift)^2) and (rows, rows_segment0)."""
+    _need_cuda(x2d, w2d)
+    P, K = x2d.shape
+    N = w2d.shape[0]
+    y = torch.empty((P, N), device=x2d.device, dtype=torch.bfloat16)
+    part, rows, rows0 = None, 0, 0
+    if want_stats:
+        r0 = c_int(0)
+        rows = _cabi.lib().ge_conv1x1_tc_partial_rows(c_longlong(P), c_longlong(int(P_split)), K, N, ctypes_byref(r0))
+        rows0 = r0.value
+        part = torch.empty((rows, 2, N), device=x2d.device, dtype=torch.float32)
+    call("ge_conv1x1_bn_stats", ptr(x2d), ptr(w2d), ptr(y), ptr(shift), ptr(part), c_longlong(P), c_longlong(int(P_split)),
+         K, N, stream(), work=(2 * P * (K + N) + 2 * K * N, 2 * P * K * N))
+    return (y, part, rows, rows0) if want_stats else y
+
+
+class _Conv1x1BnAct(Function):
+    """relu(BatchNorm2d(conv1x1(x)) + residual), training mode, bf16 NHWC: the tcgen05 GEMM writes y and the partial batch
+    statistics of y from its fp32 accumulators; finalize + apply follow (no statistics pass over y).  Backward: fused
+    BatchNorm backward, then dgrad / wgrad as two library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, residual, gamma, beta, running_mean, running_var, nbt, momentum, eps, relu, split):
+        xc = _nhwc_view(x)
+        Nb, K, H, W = xc.shape
+        Cout = weight.shape[0]
+        P = Nb * H * W
+        P_split = split * H * W if 0 < split < Nb else 0
+        nseg = 2 if P_split else 1
+        x2 = xc.permute(0, 2, 3, 1).reshape(P, K)
+        w2 = weight.reshape(Cout, K).to(torch.bfloat16).contiguous()
+        y2, part, rows, rows0 = conv1x1_gemm(x2, w2, running_mean, True, P_split)
+        y = y2.view(Nb, H, W, Cout).permute(0, 3, 1, 2)
+        rc = _nhwc_view(residual.to(torch.bfloat16)) if residual is not None else None
+        g, b = _f32c(gamma), _f32c(beta)
+        dev = x.device
+        out = torch.empty_like(y)
+        save = torch.empty((2, nseg, Cout), device=dev, dtype=torch.float32)
+        mask = torch.empty(_cabi.lib().ge_bn_relu_mask_bytes(P, Cout), device=dev, dtype=torch.uint8) if relu else None
+        call("ge_bn_fwd_train_prestat", ptr(y), ptr(rc), ptr(g), ptr(b), ptr(running_mean), ptr(running_var), ptr(nbt),
+             c_float(momentum), c_float(eps), ptr(out), ptr(save[0]), ptr(save[1]), ptr(mask), ptr(part), rows, rows0,
+             BF16, c_longlong(P), c_longlong(P_split), Cout, int(relu), stream(),
+             work=(P * Cout * 2 * (2 + (1 if rc is not None else 0)), 6 * P * Cout))
+        ctx.save_for_backward(x2, w2, y, mask, g, save)
+        ctx.cfg = (P, P_split, K, Cout, bool(relu), rc is not None, weight.shape, weight.dtype, gamma.dtype, beta.dtype, xc.shape)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x2, w2, y, mask, g, save = ctx.saved_tensors
+        P, P_split, K, Cout, relu, has_res, wshape, wdt, gdt, bdt, xshape = ctx.cfg
+        d = _nhwc_view(dout.to(torch.bfloat16))
+        dy = torch.empty_like(y)
+        dres = torch.empty_like(y) if has_res else None
+        dgb = torch.empty((2, Cout), device=d.device, dtype=torch.float32)
+        nbytes = _cabi.lib().ge_bn_workspace_bytes(P, Cout)
+        ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        call("ge_bn_bwd", ptr(d), ptr(mask), ptr(y), ptr(g), ptr(save[0]), ptr(save[1]), ptr(dy), ptr(dres), ptr(dgb[0]),
+             ptr(dgb[1]), ptr(ws), c_size_t(nbytes), BF16, c_longlong(P), c_longlong(P_split), Cout, int(relu), stream(),
+             work=(P * Cout * 2 * (3 + (1 if has_res else 0)) + (P * Cout // 8 if relu else 0), 16 * P * Cout))
+        dy2 = dy.permute(0, 2, 3, 1).reshape(P, Cout)
+        dx2 = dy2 @ w2                                            # dgrad  [P,Cout] x [Cout,K]
+        dw = (dy2.t() @ x2).float().reshape(wshape).to(wdt)       # wgrad  [Cout,P] x [P,K]
+        Nb, _, H, W = xshape
+        dx = dx2.view(Nb, H, W, K).permute(0, 3, 1, 2)
+        return dx, dw, dres, dgb[0].to(gdt), dgb[1].to(bdt), None, None, None, None, None, None, None
+
+
+def conv1x1_bn_act(x, conv, bn, residual=None, relu=True, drop_bias=False):
+    """relu(bn(conv(x)) + residual) for a 1x1, stride-1 convolution followed by a train-mode nn.BatchNorm2d on a bf16
+    NHWC map: the tcgen05 GEMM with the statistics epilogue where it applies and measures faster than cuDNN + the
+    statistics kernel (K <= 512, >= 4096 pixels; scripts/conv1x1_tc_check.py), else conv + bn_act.  `drop_bias`: the
+    caller accounts for the conv bias itself (a constant in front of train-mode BatchNorm cancels, vig._conv_bn_train)."""
+    ok = (USE_CONV1X1_TC and x.is_cuda and x.dtype == torch.bfloat16 and bn.training and type(bn) is torch.nn.BatchNorm2d
+          and bn.affine and bn.track_running_stats and bn.momentum is not None and (conv.bias is None or drop_bias)
+          and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.groups == 1 and conv.padding == (0, 0)
+          and x.dim() == 4 and conv.in_channels <= 512 and x.shape[0] * x.shape[2] * x.shape[3] >= 4096
+          and torch.is_autocast_enabled()
+          and conv1x1_tc_supported(x.shape[0] * x.shape[2] * x.shape[3], conv.in_channels, conv.out_channels)
+          and bn.num_features % 8 == 0)
+    if not ok:
+        y = torch.nn.functional.conv2d(x, conv.weight, None if drop_bias else conv.bias, conv.stride, conv.padding,
+                                       conv.dilation, conv.groups)
+        return bn_act(y, bn, residual=residual, relu=relu)
+    split = _BN_SPLIT if 0 < _BN_SPLIT < x.shape[0] else 0
+    return _Conv1x1BnAct.apply(x, conv.weight, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                               bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bool(relu), int(split))
+
+
+USE_CONV1X1_TC = True       # measured >= cuDNN + statistics kernel at every eligible shape (profiles/r2_conv1x1_tc.md)
 
 
 class _SegTail(Function):

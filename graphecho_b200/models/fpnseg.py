@@ -73,10 +73,11 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        out = GF.bn_act(self.conv1(x), self.bn1, relu=True)
+        # 1x1 convs: tcgen05 GEMM whose epilogue yields the BatchNorm statistics (bf16 path), else cuDNN + statistics pass
+        out = GF.conv1x1_bn_act(x, self.conv1, self.bn1, relu=True)
         out = GF.bn_act(self.conv2(out), self.bn2, relu=True)
         identity = x if self.downsample is None else GF.bn_act(self.downsample[0](x), self.downsample[1], relu=False)
-        return GF.bn_act(self.conv3(out), self.bn3, residual=identity, relu=True)   # BN + add + ReLU in one pass
+        return GF.conv1x1_bn_act(out, self.conv3, self.bn3, residual=identity, relu=True)   # BN + add + ReLU in one pass
 
 
 class ResNet(nn.Module):

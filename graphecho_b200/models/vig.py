@@ -224,8 +224,7 @@ def _conv_bn_train(x, conv, bn, residual=None):
     """Training-mode BatchNorm(conv(x)) without the convolution's bias passes.  A per-channel constant in front of
     train-mode BatchNorm cancels in the output and has zero gradient; it only shifts the batch mean, so the
     running mean gets its `momentum * bias` share added back (state_dict parity with the reference)."""
-    y = GF.bn_act(F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups), bn,
-                  residual=residual, relu=False)
+    y = GF.conv1x1_bn_act(x, conv, bn, residual=residual, relu=False, drop_bias=True)
     if conv.bias is not None and bn.track_running_stats:
         with torch.no_grad():
             # one running-mean update per BatchNorm segment (GF.domain_split): 1 - (1-m)^nseg of the bias in total

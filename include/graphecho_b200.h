@@ -207,6 +207,14 @@ int ge_bn_fwd_train(const void* x, const void* residual, const float* gamma, con
                     float momentum, float eps, void* out, float* save_mean, float* save_rstd,
                     void* relu_mask, void* workspace, size_t workspace_bytes,
                     int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream);
+/* The same forward for an x whose per-CTA partial statistics already exist (the epilogue of ge_conv1x1_bn_stats):
+ * finalize + apply only.  part fp32 [rows][2][C] = sums of (x - shift), (x - shift)^2 with shift = running_mean as it
+ * is before this call (0 when NULL); rows [0, rows_segment0) belong to pixels [0, P_split). */
+int ge_bn_fwd_train_prestat(const void* x, const void* residual, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, long long* num_batches_tracked,
+                            float momentum, float eps, void* out, float* save_mean, float* save_rstd,
+                            void* relu_mask, const float* part, int rows, int rows_segment0,
+                            int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream);
 int ge_bn_fwd_eval(const void* x, const void* residual, const float* gamma, const float* beta,
                    const float* running_mean, const float* running_var, float eps, void* out,
                    int dtype, long long P, int C, int relu, ge_stream_t stream);
@@ -233,6 +241,17 @@ int ge_maxpool3s2_fwd(const void* x, void* out, unsigned char* arg, int dtype,
                       int N, int H, int W, int C, ge_stream_t stream);
 int ge_maxpool3s2_bwd(const void* dout, const unsigned char* arg, void* dx, int dtype,
                       int N, int H, int W, int C, ge_stream_t stream);
+
+/* ---- f3 (first slice): 1x1 convolution as a tcgen05 GEMM with the BatchNorm statistics in its epilogue -------------
+ * Bottleneck conv1/conv3 + BatchNorm (models/fpnseg.py:192-212), Grapher fc1 (models/vig.py:402-405) on NHWC bf16 maps:
+ * y [P,N] = x [P,K] W[N,K]^T (fp32 accumulate in TMEM, TMA-staged operands, weight tile resident in shared memory,
+ * persistent CTAs).  part (or NULL) receives [rows][2][N] fp32 partial sums of (y - shift[n]) and (y - shift[n])^2 taken
+ * from the fp32 accumulators -- the input of ge_bn_fwd_train_prestat; rows = ge_conv1x1_tc_partial_rows(...).
+ * Supported: K % 64 == 0, N % 64 == 0, min(N,256) * K * 2 <= 128 KB (or a narrower column tile that fits). */
+int ge_conv1x1_tc_supported(long long P, int K, int N);
+int ge_conv1x1_tc_partial_rows(long long P, long long P_split, int K, int N, int* rows_segment0);
+int ge_conv1x1_bn_stats(const void* x, const void* w, void* y, const float* shift, float* part,
+                        long long P, long long P_split, int K, int N, ge_stream_t stream);
 
 /* ---- K6: the TGCN recurrence as one persistent launch ---------------------------------------------
  * TGCN.forward's time loop (models/TGCN.py:224-235) over DyGraphConv2d.forward (:62-78) AFTER the state-independent

@@ -687,3 +687,67 @@ def test_mask_boxes_vs_oracle(dev):
     assert torch.equal(GF.mask_boxes(score.to(dev)).cpu(), ref)
     # raw logits used as a score map (the temporal branch, Appendix A-12): every plane is "full"
     assert torch.equal(GF.mask_boxes(logits.to(dev)).cpu(), torch.stack(GM.find_bbox(logits)))
+
+
+# ---------------------------------------------------------------------------------------- f3: tcgen05 1x1-conv GEMM + BN statistics
+@pytest.mark.parametrize("N,H,Ci,Co,ns,res", [(16, 28, 64, 256, 8, True), (16, 28, 256, 64, 6, False), (12, 28, 256, 256, 0, False),
+                                              (32, 14, 512, 128, 16, False), (32, 14, 128, 512, 11, True), (40, 11, 64, 64, 13, False)])
+def test_conv1x1_tc_gemm_with_bn_statistics(dev, N, H, Ci, Co, ns, res):
+    """1x1 conv + train-mode BatchNorm (+ residual) + ReLU on the tcgen05 GEMM whose epilogue produces the batch statistics
+    (Bottleneck conv1/conv3, fpnseg.py:192-212), bf16 operands, against nn.Conv2d + nn.BatchNorm2d in fp32 on the SAME
+    bf16-rounded inputs and weights: output (bf16 round-off), every gradient, running statistics (two updates under a
+    domain split), and -- the epilogue itself -- the GEMM output and the partial sums it reports."""
+    import copy
+    torch.manual_seed(Ci + Co + H)
+    P = N * H * H
+    assert GF.conv1x1_tc_supported(P, Ci, Co)
+    x = torch.randn(N, Ci, H, H).bfloat16().float()
+    r = torch.randn(N, Co, H, H).bfloat16().float() if res else None
+    conv = torch.nn.Conv2d(Ci, Co, 1, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+    bn = torch.nn.BatchNorm2d(Co)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.1 * torch.randn(Co)); bn.bias.copy_(0.1 * torch.randn(Co))
+        bn.running_mean.copy_(0.05 * torch.randn(Co)); bn.running_var.copy_(1 + 0.1 * torch.rand(Co))
+    conv_d, bn_d = copy.deepcopy(conv).to(dev), copy.deepcopy(bn).to(dev)
+    # the raw GEMM and its partial statistics
+    x2 = x.to(dev).bfloat16().permute(0, 2, 3, 1).reshape(P, Ci).contiguous()
+    w2 = conv.weight.reshape(Co, Ci).to(dev).bfloat16().contiguous()
+    shift = bn.running_mean.to(dev)
+    Ps = ns * H * H
+    y, part, rows, rows0 = GF.conv1x1_gemm(x2, w2, shift, True, Ps)
+    yref = x2.float() @ w2.float().t()
+    close(y, yref, rtol=1e-2, atol=2e-2)                                   # bf16 output rounding
+    d = yref - shift
+    segs = [(d[:Ps], part[:rows0])] + ([(d[Ps:], part[rows0:])] if 0 < Ps < P else [])
+    if not (0 < Ps < P):
+        segs = [(d, part)]
+    for dd, pp in segs:
+        close(pp[:, 0].sum(0), dd.sum(0), rtol=1e-4, atol=1e-2)
+        close(pp[:, 1].sum(0), (dd * dd).sum(0), rtol=1e-4, atol=1e-2)
+    # the fused module path
+    xo = x.clone().requires_grad_()
+    ro = r.clone().requires_grad_() if res else None
+    yc = conv(xo)
+    yb = torch.cat([bn(yc[:ns]), bn(yc[ns:])]) if 0 < ns < N else bn(yc)
+    ref = torch.relu(yb + ro if res else yb)
+    W = torch.randn_like(ref)
+    (ref * W).sum().backward()
+    cl = torch.channels_last
+    xd = x.to(dev).bfloat16().contiguous(memory_format=cl).requires_grad_()
+    rd = r.to(dev).bfloat16().contiguous(memory_format=cl).requires_grad_() if res else None
+    with torch.autocast("cuda", dtype=torch.bfloat16), GF.domain_split(ns):
+        out = GF.conv1x1_bn_act(xd, conv_d, bn_d, residual=rd, relu=True)
+    assert out.dtype == torch.bfloat16
+    close(out, ref, rtol=2e-2, atol=4e-2)
+    (out.float() * W.to(dev)).sum().backward()
+    relerr = lambda a, b: float((a.detach().float().cpu() - b).norm() / b.norm())
+    assert relerr(xd.grad, xo.grad) < 3e-2
+    assert relerr(conv_d.weight.grad, conv.weight.grad) < 3e-2
+    assert relerr(bn_d.weight.grad, bn.weight.grad) < 3e-2 and relerr(bn_d.bias.grad, bn.bias.grad) < 3e-2
+    if res:
+        assert relerr(rd.grad, ro.grad) < 3e-2
+    close(bn_d.running_mean, bn.running_mean, rtol=1e-3, atol=2e-3)
+    close(bn_d.running_var, bn.running_var, rtol=2e-3, atol=2e-3)
+    assert int(bn_d.num_batches_tracked) == (2 if 0 < ns < N else 1)
