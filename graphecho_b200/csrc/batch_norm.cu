@@ -371,7 +371,7 @@ bn_apply_bwd4_kernel(const T* __restrict__ dy, const unsigned short* __restrict_
 int bn_chunks(long long P, int C) {
     const int nPL = BN_THREADS / (C / 8);
     long long want = P / ((long long)nPL * 8);           // >= 8 pixels per pixel-lane
-    const long long cap = (long long)ge::sm_count() * 2;       // <= 296 partial rows: one trip of the finalize lanes
+    const long long cap = (long long)ge::sm_count() * 4;       // 592 partial rows: two trips of the finalize lanes
     if (want > cap) want = cap;
     if (want < 2) want = 2;                              // room for one chunk per segment
     return (int)want;
