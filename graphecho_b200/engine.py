@@ -80,31 +80,62 @@ def shard_range(n_items: int, rank: int, world: int) -> range:
     return range(start, start + base + (1 if rank < rem else 0))
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
 class FlatGradSync:
-    """The DDP exchange as ONE all-reduce(AVG) per step over a flat fp32 buffer, no buckets, no hooks, tolerant
-    of parameters that did not take part in the step (their slice is zero).
+    """The DDP exchange over a flat fp32 buffer, no per-parameter hooks, tolerant of parameters that did not take part
+    in the step (their slice is zero).  The buffer is laid out in BUCKETS (lists of parameters given by the caller in
+    the order their gradients become final); `reduce_bucket(i)` packs bucket i and starts its all-reduce(AVG) on a
+    communication stream while the rest of the backward is still running, `all_reduce()` reduces whatever is left and
+    waits for everything.  With one bucket this is ONE all-reduce per step after the backward.
 
     bind=True : every parameter's .grad is a strided view of the flat buffer for the whole run (autograd
                 accumulates into it: one small add kernel per parameter per step).
     bind=False: .grad is left to autograd (set to None each step, so the first gradient is adopted without a
                 copy -- 343 fewer launches per step for the config-2 engine); only when world_size > 1 are the
-                gradients packed into the flat buffer (one multi-tensor copy), reduced, and handed back as views.
+                gradients packed into the flat buffer (one multi-tensor copy per bucket), reduced, and handed back as views.
     """
 
-    def __init__(self, modules, group=None, bind=True):
-        self.params = [p for m in modules for p in m.parameters() if p.requires_grad]
+    def __init__(self, modules, group=None, bind=True, buckets=None):
+        every = [p for m in modules for p in m.parameters() if p.requires_grad]
+        if buckets is None:
+            buckets = [every]
+        else:
+            seen = {id(p) for b in buckets for p in b}
+            rest = [p for p in every if id(p) not in seen]
+            buckets = [[p for p in b if p.requires_grad] for b in buckets] + ([rest] if rest else [])
+            assert sum(len(b) for b in buckets) == len(every), "buckets must partition the parameters"
+        self.buckets = buckets
+        self.params = [p for b in buckets for p in b]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.bind = bind
-        self.views, off = [], 0
-        for p in self.params:
-            self.views.append(self._view(p, off))
-            off += p.numel()
+        self.views, self.bucket_range, off = [], [], 0
+        for b in buckets:
+            start = off
+            for p in b:
+                self.views.append(self._view(p, off))
+                off += p.numel()
+            self.bucket_range.append((start, off))
+        self._bucket_slice = []
+        i = 0
+        for b in buckets:
+            self._bucket_slice.append((i, i + len(b)))
+            i += len(b)
         if bind:
             for p, v in zip(self.params, self.views):
                 p.grad = v
         self.group = group
+        self._done = [False] * len(buckets)
+        self._pending = []
+        self._comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
 
     def _view(self, p, off):
         """A gradient view with the parameter's own (dense, possibly channels_last) strides, which is
@@ -115,6 +146,7 @@ class FlatGradSync:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
     def zero(self):
+        self._done = [False] * len(self.buckets)
         if self.bind:
             self.flat.zero_()
         else:
@@ -131,16 +163,43 @@ class FlatGradSync:
                     view.copy_(p.grad)
                 p.grad = view
 
-    def pack(self):
-        """bind=False: copy the gradients autograd produced into the flat buffer (absent ones as zeros)."""
-        self.flat.zero_()
-        dst = [v for p, v in zip(self.params, self.views) if p.grad is not None]
-        src = [p.grad for p in self.params if p.grad is not None]
+    def _pack_bucket(self, i):
+        lo, hi = self.bucket_range[i]
+        a, b = self._bucket_slice[i]
+        self.flat[lo:hi].zero_()
+        dst = [v for p, v in zip(self.params[a:b], self.views[a:b]) if p.grad is not None]
+        src = [p.grad for p in self.params[a:b] if p.grad is not None]
         if src:
             torch._foreach_copy_(dst, src)
+
+    def pack(self):
+        """bind=False: copy the gradients autograd produced into the flat buffer (absent ones as zeros)."""
+        for i in range(len(self.buckets)):
+            self._pack_bucket(i)
         return self.flat
 
+    def reduce_bucket(self, i, after=()):
+        """Start the exchange of bucket i now (its gradients are final): pack + all-reduce on the communication stream,
+        ordered after the current stream and the streams in `after`.  No-op for one rank."""
+        if self._done[i] or self._world() <= 1:
+            return
+        self._done[i] = True
+        lo, hi = self.bucket_range[i]
+        piece = self.flat[lo:hi]
+        nccl = dist.get_backend(self.group) == "nccl"
+        comm = self._comm
+        if comm is not None:
+            comm.wait_stream(torch.cuda.current_stream())
+            for s_ in after:
+                comm.wait_stream(s_)
+        with torch.cuda.stream(comm) if comm is not None else _NullCtx():
+            if not self.bind:
+                self._pack_bucket(i)
+            work = dist.all_reduce(piece, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._pending.append((work, piece, nccl))
+
     def all_reduce(self):
+        """Exchange every bucket that has not been started, wait for all of them, and hand the reduced gradients back."""
         if self._world() <= 1:
             if not self.bind:
                 # parameters that took no part in the step step on a zero gradient (their untouched, all-zero
@@ -149,13 +208,15 @@ class FlatGradSync:
                     if p.grad is None:
                         p.grad = v
             return
-        if not self.bind:
-            self.pack()
-        if dist.get_backend(self.group) == "nccl":
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
-        else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.div_(self._world())
+        for i in range(len(self.buckets)):
+            self.reduce_bucket(i)
+        for work, piece, nccl in self._pending:
+            work.wait()
+            if not nccl:
+                piece.div_(self._world())
+        self._pending = []
+        if self._comm is not None:
+            torch.cuda.current_stream().wait_stream(self._comm)
         if not self.bind:
             for p, v in zip(self.params, self.views):     # every rank steps every parameter identically
                 p.grad = v
@@ -184,14 +245,6 @@ def init_distributed(device_index: int | None = None):
     return rank, local, world
 
 
-class _NullCtx:
-    def __enter__(self):
-        return None
-
-    def __exit__(self, *exc):
-        return False
-
-
 class _JointDiscriminator(nn.Module):
     """Discriminator fed the whole [source | target] feature map of a level (no slice + cat)."""
 
@@ -205,15 +258,27 @@ class _JointDiscriminator(nn.Module):
         return self.dis.forward_joint(feature_all, ns)
 
 
-class _Trunk(nn.Module):
-    """FPN backbone + pyramid as its own callable (its own CUDA graph): x -> (p2, p3, p4, p5)."""
+class _TrunkLower(nn.Module):
+    """FPN backbone up to c4 as its own callable (its own CUDA graph): x -> (c2, c3, c4)."""
 
     def __init__(self, fpn):
         super().__init__()
         self.fpn = fpn
 
     def forward(self, x):
-        return self.fpn.forward_trunk(x)
+        return self.fpn.forward_trunk_lower(x)
+
+
+class _TrunkUpper(nn.Module):
+    """Last backbone stage + pyramid: (c2, c3, c4) -> (p2, p3, p4, p5).  Separate from the lower part so that its
+    gradients (2/3 of the backbone's parameters) are final -- and on the wire -- while the lower part's backward runs."""
+
+    def __init__(self, fpn):
+        super().__init__()
+        self.fpn = fpn
+
+    def forward(self, c2, c3, c4):
+        return self.fpn.forward_trunk_upper(c2, c3, c4)
 
 
 class _Head(nn.Module):
@@ -237,8 +302,8 @@ class UDAEngine:
         self.network = self.network.to(memory_format=torch.channels_last)
         if world_size > 1 and cfg.sync_bn:
             self.network = nn.SyncBatchNorm.convert_sync_batchnorm(self.network)
-        self._trunk_raw, self._head_raw = _Trunk(self.network), _Head(self.network)
-        self._trunk, self._head = self._trunk_raw, self._head_raw
+        self._lower_raw, self._upper_raw, self._head_raw = _TrunkLower(self.network), _TrunkUpper(self.network), _Head(self.network)
+        self._lower, self._upper, self._head = self._lower_raw, self._upper_raw, self._head_raw
         self.aux: dict[str, nn.Module] = {}
         self._gmodule = None
         if cfg.graph_matching:
@@ -262,7 +327,14 @@ class UDAEngine:
         modules = [self.network, *self.aux.values()]
         for m in modules:
             m.train()
-        self.grads = FlatGradSync(modules, bind=False)
+        # gradient buckets in the order they become final in the phased step: (0) discriminators, graph module, FPN head;
+        # (1) Grapher + upper trunk; (2) the rest (lower trunk, TGCN).  Each is all-reduced as soon as it is final.
+        early = [p for n_, m in self.aux.items() if n_.startswith("Dis_") or n_ == "Graph" for p in m.parameters()]
+        early += self.network.head_parameters()
+        mid = [p for n_, m in self.aux.items() if n_ == "Grapher" for p in m.parameters()] + self.network.upper_trunk_parameters()
+        self.grads = FlatGradSync(modules, bind=False, buckets=[early, mid])
+        self._early_exchange = (world_size > 1 and cfg.phased_backward and cfg.graph_matching and not cfg.temporal_graph
+                                and os.environ.get("GE_EARLY_EXCHANGE", "1") != "0")
         self.graphed = False
         # high priority: the graph module's hundreds of tiny kernels (and the two read-backs its host code waits on)
         # must not queue behind the waves of the discriminator / head kernels they overlap with
@@ -302,7 +374,10 @@ class UDAEngine:
         # make_graphed_callables shares one memory pool between the graphs and relies on them being replayed in
         # the order of this tuple (forward) and in its reverse (backward): trunk -> Grapher -> head -> discriminators
         # forward, discriminators -> head -> Grapher -> trunk backward -- the order every step below keeps.
-        calls, samples, names = [self._trunk_raw], [(x,)], ["trunk"]
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=cfg.bf16), self._split(ns):
+            mids = self._lower_raw(x)
+        calls, samples, names = [self._lower_raw, self._upper_raw], [(x,), tuple(torch.zeros_like(m).requires_grad_() for m in mids)], ["lower", "upper"]
+        del mids
         if cfg.graph_matching and cfg.vig_grapher:
             calls.append(self.aux["Grapher"])
             samples.append((torch.zeros_like(feats[0]).requires_grad_(),))
@@ -325,8 +400,10 @@ class UDAEngine:
         # 3 warm-up executions + 1 capture of every segment's forward and backward
         self.graph_launches = (_cabi.launch_count() - before) // 4
         for name, g in zip(names, graphed):
-            if name == "trunk":
-                self._trunk = g
+            if name == "lower":
+                self._lower = g
+            elif name == "upper":
+                self._upper = g
             elif name == "head":
                 self._head = g
             else:
@@ -400,7 +477,7 @@ class UDAEngine:
         ns = self._prepare(frames_src, frames_tgt)
         losses = {}
         with self._autocast(), self._split(ns):
-            feats = list(self._trunk(torch.cat([frames_src, frames_tgt], dim=0)))
+            feats = list(self._upper(*self._lower(torch.cat([frames_src, frames_tgt], dim=0))))
             p2g = self.aux["Grapher"](feats[0]) if cfg.graph_matching and cfg.vig_grapher else None
         with self._autocast():
             logits = self._head(*feats)
@@ -473,7 +550,9 @@ class UDAEngine:
         if side is not None:
             side.wait_stream(main)          # inputs (e.g. the step's host->device copies) are ready for the side stream
         with self._autocast(), self._split(ns):
-            feats = list(self._trunk(torch.cat([frames_src, frames_tgt], dim=0)))
+            lower = self._lower(torch.cat([frames_src, frames_tgt], dim=0))
+            leaves_u = [t.detach().requires_grad_() for t in lower]
+            feats = list(self._upper(*leaves_u))
             tops = list(feats)
             if cfg.vig_grapher:
                 tops[0] = self.aux["Grapher"](feats[0])
@@ -511,6 +590,8 @@ class UDAEngine:
                 torch.autograd.backward(list(mid.values()))
         if side is not None:
             main.wait_stream(side)
+        if self._early_exchange:
+            self.grads.reduce_bucket(0)         # discriminators, graph module, head: final; on the wire under the trunk backward
         # 4. join the pyramid gradients and run the trunk (and Grapher) backward
         out_t, out_g = [], []
         for i, f in enumerate(feats):
@@ -528,7 +609,11 @@ class UDAEngine:
                 if g_top is not None:
                     out_t.append(tops[i])
                     out_g.append(g_top)
-        torch.autograd.backward(out_t, out_g)
+        with self._split(ns):
+            torch.autograd.backward(out_t, out_g)                     # Grapher + upper trunk: stops at leaves_u
+            if self._early_exchange:
+                self.grads.reduce_bucket(1)                           # 2/3 of the backbone: on the wire under the lower backward
+            torch.autograd.backward(list(lower), [l.grad for l in leaves_u])
         # everything is issued: the seed-bank update (next step's input) runs while the GPU finishes the backward
         with torch.cuda.stream(side) if side is not None else _NullCtx():
             self._gmodule.flush_seed_update()

@@ -46,15 +46,27 @@ class VGG16(nn.Module):
                 if m.bias is not None:
                     m.bias.detach().zero_()
 
-    def forward(self, x):
+    def _blocks(self, x, first, last):
         feats = []
-        for b in range(1, 6):
+        for b in range(first, last + 1):
             mods = list(getattr(self, f"block_{b}"))
             for i in range(0, len(mods) - 1, 3):          # (conv, BN, ReLU) triples -> conv + fused BN+ReLU
                 x = GF.bn_act(mods[i](x), mods[i + 1], relu=True)
             x = mods[-1](x)                                # max-pool
             feats.append(x)
         return feats
+
+    def forward_lower(self, x):
+        """blocks 1-4 -> [c1, c2, c3, c4]"""
+        return self._blocks(x, 1, 4)
+
+    def forward_upper(self, c4):
+        """block 5 -> c5"""
+        return self._blocks(c4, 5, 5)[0]
+
+    def forward(self, x):
+        feats = self.forward_lower(x)
+        return feats + [self.forward_upper(feats[-1])]
 
 
 class Bottleneck(nn.Module):
@@ -117,14 +129,23 @@ class ResNet(nn.Module):
                 m.weight.data.fill_(1)
                 m.bias.data.zero_()
 
-    def forward(self, x):
+    def forward_lower(self, x):
+        """stem + layer1-3 -> [c1, c2, c3, c4]"""
         x = GF.bn_act(self.conv1(x), self.bn1, relu=True)
         x = GF.maxpool3s2(x) if x.shape[1] % 8 == 0 else self.maxpool(x)
         feats = [x]
-        for stage in (self.layer1, self.layer2, self.layer3, self.layer4):
+        for stage in (self.layer1, self.layer2, self.layer3):
             x = stage(x)
             feats.append(x)
         return feats
+
+    def forward_upper(self, c4):
+        """layer4 -> c5"""
+        return self.layer4(c4)
+
+    def forward(self, x):
+        feats = self.forward_lower(x)
+        return feats + [self.forward_upper(feats[-1])]
 
 
 def ResNet50(in_channel=3, pretrained=True):
@@ -173,6 +194,34 @@ class FPN(nn.Module):
 
     def _upsample_add(self, x, y):
         return GF.upsample_add(x, y)
+
+    def forward_trunk_lower(self, x):
+        """First part of forward_trunk: the backbone up to c4 -> (c2, c3, c4).  The engine runs (and captures) the trunk
+        in two parts so that the gradients of the upper part -- 2/3 of the backbone's parameters sit in its last stage
+        -- can be all-reduced while the lower part's backward is still running."""
+        _need_cuda(x)
+        x = x.contiguous(memory_format=torch.channels_last)
+        _, c2, c3, c4 = self.back_bone.forward_lower(x)
+        return c2, c3, c4
+
+    def forward_trunk_upper(self, c2, c3, c4):
+        """Second part: last backbone stage + lateral / top-down pyramid -> (p2, p3, p4, p5)."""
+        c5 = self.back_bone.forward_upper(c4)
+        p5 = self.toplayer(c5)
+        p4 = GF.upsample_add(p5, self.latlayer1(c4))
+        p3 = GF.upsample_add(p4, self.latlayer2(c3))
+        p2 = GF.upsample_add(p3, self.latlayer3(c2))
+        return p2, p3, p4, p5
+
+    def upper_trunk_parameters(self):
+        """Parameters of forward_trunk_upper (last backbone stage, top and lateral layers)."""
+        last = self.back_bone.layer4 if hasattr(self.back_bone, "layer4") else self.back_bone.block_5
+        mods = [last, self.toplayer, self.latlayer1, self.latlayer2, self.latlayer3]
+        return [p for m in mods for p in m.parameters()]
+
+    def head_parameters(self):
+        mods = [self.smooth1, self.smooth2, self.smooth3, self.semantic_branch, self.conv2, self.conv3, self.gn1, self.gn2]
+        return [p for m in mods for p in m.parameters()]
 
     def forward_trunk(self, x):
         """Backbone + lateral / top-down pyramid (fpnseg.py:391-423): x -> [p2, p3, p4, p5] (pre-smoothing,

@@ -101,3 +101,41 @@ def test_flat_grad_allreduce_matches_single_process():
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _worker_buckets(rank, world, port, out):
+    """Bucketed exchange: the last layer's gradients are final first (backward order) and go on the wire with
+    reduce_bucket(0) before the rest; all_reduce() then exchanges the remaining bucket and hands every gradient back."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    unused = torch.nn.Linear(3, 3)
+    sync = FlatGradSync([net, unused], bind=False, buckets=[list(net[2].parameters())])     # rest = net[0] + unused
+    ok = len(sync.buckets) == 2 and sync.bucket_range[0] == (0, 12) and sync.nbytes == 4 * (12 + 35 + 12)
+    full = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+    tgt = torch.randn(8, 2, generator=torch.Generator().manual_seed(2))
+    idx = list(shard_range(8, rank, world))
+    for _ in range(2):
+        sync.zero()
+        hid = net[1](net[0](full[idx]))
+        leaf = hid.detach().requires_grad_()
+        ((net[2](leaf) - tgt[idx]) ** 2).mean().backward()          # last layer only
+        sync.reduce_bucket(0)                                        # its gradients are final: start their exchange
+        hid.backward(leaf.grad)                                      # the rest of the backward
+        sync.all_reduce()
+        ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        ref.load_state_dict(net.state_dict())
+        ((ref(full) - tgt) ** 2).mean().backward()
+        ok = ok and all(torch.allclose(p.grad, q.grad, atol=1e-6) for p, q in zip(net.parameters(), ref.parameters()))
+        ok = ok and float(unused.weight.grad.abs().sum()) == 0.0
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_bucketed_grad_exchange_matches_single_process():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_buckets, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
