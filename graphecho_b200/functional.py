@@ -888,6 +888,30 @@ def mask_boxes(maps):
     return boxes
 
 
+@torch.no_grad()
+def sampler_labels(boxes, level_hw, strides, size_ranges):
+    """Labels of every location of every pyramid level + per-level (positive, negative) counts in one launch
+    (graph_matching.py:609-635, 874-959).  boxes [B,K,4] fp32; level_hw [(h,w)...]; strides, size_ranges per level.
+    Returns ([labels_l int64 [B*h_l*w_l]], counts int32 [L,2] on the device)."""
+    import ctypes
+    _need_cuda(boxes)
+    bx = _f32c(boxes)
+    B, K = bx.shape[0], bx.shape[1]
+    L = len(level_hw)
+    sizes = [int(h) * int(w) for h, w in level_hw]
+    labels = torch.empty(B * sum(sizes), device=bx.device, dtype=torch.int64)
+    counts = torch.zeros((L, 2), device=bx.device, dtype=torch.int32)
+    IA, FA = ctypes.c_int * L, ctypes.c_float * L
+    call("ge_sampler_labels", ptr(bx), ptr(labels), ptr(counts), IA(*[int(h) for h, _ in level_hw]), IA(*[int(w) for _, w in level_hw]),
+         IA(*[int(s_) for s_ in list(strides)[:L]]), FA(*[float(a) for a, _ in size_ranges]), FA(*[float(b) for _, b in size_ranges]),
+         L, B, K, stream(), work=(16 * B * K + 8 * labels.numel(), 20 * K * labels.numel()))
+    out, off = [], 0
+    for n_ in sizes:
+        out.append(labels[off * B:(off + n_) * B])
+        off += n_
+    return out, counts
+
+
 class _GradReverse(Function):
     """Gradient reversal (gradient_reversal.py:6-24) without the reference's full clone()."""
 

@@ -155,7 +155,8 @@ class GModule(nn.Module):
         still running.  The next training forward consumes the result (train_cardiac_uda.py:247-256 calls the
         graph module with the same masks)."""
         shapes = [torch.empty((0, 0, int(h), int(w)), device=device) for h, w in feature_shapes]
-        plan = self.graph_generator.plan(self.compute_locations(shapes), self.find_bbox(targets))
+        plan = self.graph_generator.plan(self.compute_locations(shapes), self.find_bbox(targets),
+                                         [(int(h), int(w)) for h, w in feature_shapes], self.fpn_strides)
         self._prepared_source = (targets, plan[0], plan[1].tolist())
 
     def flush_seed_update(self):
@@ -174,12 +175,13 @@ class GModule(nn.Module):
         (feat_s, off_s), (feat_t, off_t) = src, tgt
         gen = self.graph_generator
         prepared, self._prepared_source = getattr(self, "_prepared_source", None), None
-        plan_t = gen.plan(self.compute_locations(feat_t), self.find_bbox(score_maps))
+        geo = [(int(f.size(-2)), int(f.size(-1))) for f in feat_t]
+        plan_t = gen.plan(self.compute_locations(feat_t), self.find_bbox(score_maps), geo, self.fpn_strides)
         if prepared is not None and prepared[0] is targets:
             labels_s, counts_s = prepared[1], prepared[2]
             counts_t = plan_t[1].tolist()                                           # host sync: target counts only
         else:
-            plan_s = gen.plan(self.compute_locations(feat_s), self.find_bbox(targets))
+            plan_s = gen.plan(self.compute_locations(feat_s), self.find_bbox(targets), geo, self.fpn_strides)
             labels_s = plan_s[0]
             counts_s, counts_t = torch.stack([plan_s[1], plan_t[1]]).tolist()       # ONE host sync for both domains
         nodes_1, labels_1, weights_1 = gen.gather(feat_s, labels_s, counts_s, off_s)
@@ -506,9 +508,13 @@ class PrototypeComputation(object):
         labels[amin == INF] = 0
         return labels
 
-    def plan(self, locations, boxes):
+    def plan(self, locations, boxes, level_hw=None, strides=None):
         """Device-side half of the sampler: per-level label maps + the [levels, 2] (positive, negative)
-        counts the host needs.  No synchronisation."""
+        counts the host needs.  No synchronisation.  With the level geometry (`level_hw`, `strides`) and CUDA boxes this
+        is ONE kernel launch (ge_sampler_labels); otherwise the vectorised torch route."""
+        if level_hw is not None and torch.is_tensor(boxes) and boxes.is_cuda and boxes.shape[1] <= 8 and len(level_hw) <= 5:
+            sizes = [[-1, 64], [64, 128], [128, 256], [256, 512], [512, INF]]
+            return GF.sampler_labels(boxes, level_hw, strides, sizes[:len(level_hw)])
         labels = [l.reshape(-1) for l in self.prepare_targets(locations, boxes)]
         counts = torch.stack([torch.stack([(l > 0).sum(), (l == 0).sum()]) for l in labels])
         return labels, counts

@@ -288,6 +288,17 @@ int ge_seg_loss_bwd(const float* logits, const float* target, const float* numde
  * (train_cardiac_uda.py:235) straight from the logits, without materialising the score map. */
 int ge_mask_boxes(const void* maps, float* boxes, int dtype, int planes, int H, int W, int mode, ge_stream_t stream);
 
+/* ---- node sampler, device half ------------------------------------------------------------------------
+ * PrototypeComputation.prepare_targets / compute_targets_for_locations over GModule.compute_locations
+ * (models/graph_matching.py:609-635, 874-959): the label of every location of every pyramid level (smallest-area class
+ * box that strictly contains the location and whose largest side distance lies in the level's size range; else 0) and the
+ * per-level (positive, negative) counts, one launch per domain.  boxes fp32 [B,K,4] (ge_mask_boxes), K <= 8, levels <= 5;
+ * labels int64 [B * sum_l h_l*w_l], level-major / image-major inside a level; counts int32 [levels][2], ZERO-FILLED by the
+ * caller.  heights / widths / strides / size_lo / size_hi are HOST arrays of length `levels`. */
+int ge_sampler_labels(const float* boxes, long long* labels, int* counts, const int* heights, const int* widths,
+                      const int* strides, const float* size_lo, const float* size_hi, int levels, int B, int K,
+                      ge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -751,3 +751,26 @@ def test_conv1x1_tc_gemm_with_bn_statistics(dev, N, H, Ci, Co, ns, res):
     close(bn_d.running_mean, bn.running_mean, rtol=1e-3, atol=2e-3)
     close(bn_d.running_var, bn.running_var, rtol=2e-3, atol=2e-3)
     assert int(bn_d.num_batches_tracked) == (2 if 0 < ns < N else 1)
+
+
+@pytest.mark.parametrize("hw,nc,B", [(256, 3, 4), (112, 2, 6), (256, 4, 3)])
+def test_sampler_labels_kernel_bit_exact(dev, hw, nc, B):
+    """Per-location labels of all pyramid levels + per-level (positive, negative) counts in one launch
+    (graph_matching.py:609-635, 874-959) against the oracle: bit-exact integer output, incl. the reference's stride quirk
+    (locations at 8,16,32,64 on a stride-4..32 pyramid), an empty class plane and raw-logit score maps (every box = the
+    full image -> every label 0, Appendix A-12)."""
+    from oracle import gmodule_ops as GM
+    from graphecho_b200 import synth
+    feats = synth.pyramid(B, hw, seed=1)
+    level_hw = [(f.shape[-2], f.shape[-1]) for f in feats]
+    masks = synth.disc_masks(B, nc, hw)
+    masks[1, 1] = 0
+    logits = torch.randn(B, nc, hw, hw)
+    for m in (masks, torch.where(torch.sigmoid(logits - 1.0) > 0.5, 1, 0), logits):
+        boxes = torch.stack(GM.find_bbox(m))
+        ref = GM.location_labels(GM.compute_locations(feats), list(boxes), nc)
+        labels, counts = GF.sampler_labels(boxes.to(dev), level_hw, [8, 16, 32, 64, 128][:4],
+                                           [[-1, 64], [64, 128], [128, 256], [256, 512]])
+        for l, (a, b) in enumerate(zip(labels, ref)):
+            assert torch.equal(a.cpu(), b.reshape(-1).long()), l
+            assert counts[l].tolist() == [int((b > 0).sum()), int((b == 0).sum())]
