@@ -40,6 +40,7 @@ _SIGNATURES = {
     "ge_knn_graph_nmajor": (c_int, [P, P, I, P, P, Z, I, I, I, I, I, I, P]),
     "ge_mrconv_gather_nmajor_fwd": (c_int, [P, P, P, P, P, I, I, I, I, I, I, P]),
     "ge_mrconv_gather_nmajor_bwd": (c_int, [P, P, P, P, P, I, I, I, I, I, I, P]),
+    "ge_mrconv_gather_nmajor_bwd_self": (c_int, [P, P, P, P, I, I, I, I, I, P]),
     "ge_mrconv_gather_fwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "ge_mrconv_gather_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "ge_tgcn_pool_concat_fwd": (c_int, [P, L, P, I, L, I, I, I, I, I, I, P]),

@@ -208,6 +208,127 @@ mr_gather_nmajor_bwd_scatter_kernel(const T* __restrict__ dout, const long long*
     }
 }
 
+// Self-graph backward in ONE launch, gather form, no floating-point atomics (fp32 shared-memory atomics are CAS spin
+// loops on sm_100: the first, scatter-into-shared version of this kernel spent its time in ATOMS.CAST.SPIN).
+// A CTA owns (frame b, 64-channel slab).  It stages the slab's dout_xj values (bf16/fp32) and arg-max slots in shared
+// memory, builds the REVERSE neighbour lists of the frame there (integer atomics), and then every (node j, 8 channels)
+// item sums its own term dout_x - dout_xj and the dout_xj of every node whose arg-max neighbour in that channel is j.
+// dx is written once, in the activation dtype.  Replaces init (205 MB fp32 written) + global-atomic scatter (474 MB
+// read, ncu) + a cast pass.
+constexpr int MRB_CS = 32;          // channels per slab (2 CTAs per SM at N = 784: the phases of one overlap the other)
+constexpr int MRB_THREADS = 512;
+constexpr int MRB_U = 2;            // items in flight per thread
+
+template <typename T>
+__global__ void __launch_bounds__(MRB_THREADS, 2)
+mr_gather_nmajor_bwd_self_kernel(const T* __restrict__ dout, const long long* __restrict__ idx0,
+                                 const unsigned char* __restrict__ argk, T* __restrict__ dx, int C, int N, int k) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    T* gj = reinterpret_cast<T*>(raw);                                             // [N][64] dout_xj of the slab
+    unsigned char* ak = raw + (size_t)N * MRB_CS * sizeof(T);                      // [N][64] arg-max slots
+    int* cnt = reinterpret_cast<int*>(ak + (size_t)N * MRB_CS);                    // [N+1] incoming-edge counts -> offsets
+    int* fill = cnt + (N + 1);                                                     // [N] fill cursors
+    unsigned short* src = reinterpret_cast<unsigned short*>(fill + N);             // [N*k] source node of an incoming edge
+    unsigned char* slot = reinterpret_cast<unsigned char*>(src + (size_t)N * k);   // [N*k] its neighbour slot
+    __shared__ int wsum[MRB_THREADS / 32];
+    const int b = blockIdx.y, c0 = blockIdx.x * MRB_CS, tid = threadIdx.x;
+    const long long p0 = (long long)b * N;
+    constexpr int OCT = MRB_CS / 8;
+    const int total = N * OCT;
+    for (int i = tid; i <= N; i += MRB_THREADS) cnt[i] = 0;
+    __syncthreads();
+    // ---- stage dout_xj + arg-max slots of the slab; count incoming edges.  MRB_U items per thread in flight: one CTA
+    // per SM has to keep ~64 KB of loads outstanding on its own to stream at HBM rate.
+    for (int base = tid; base < total; base += MRB_THREADS * MRB_U) {
+        float a[MRB_U][8], bq[MRB_U][8];
+        unsigned long long pk[MRB_U];
+#pragma unroll
+        for (int u = 0; u < MRB_U; ++u) {
+            const int e = base + u * MRB_THREADS;
+            if (e < total) {
+                const int i = e / OCT, c = c0 + (e - i * OCT) * 8;
+                ge::load8<T>(dout + (p0 + i) * 2 * C + 2 * c, a[u]);
+                ge::load8<T>(dout + (p0 + i) * 2 * C + 2 * c + 8, bq[u]);
+                pk[u] = *reinterpret_cast<const unsigned long long*>(argk + (p0 + i) * C + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MRB_U; ++u) {
+            const int e = base + u * MRB_THREADS;
+            if (e < total) {
+                const int i = e / OCT, cl = (e - i * OCT) * 8;
+                float g[8], own[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    g[q] = a[u][2 * q + 1]; g[4 + q] = bq[u][2 * q + 1];
+                    own[q] = a[u][2 * q] - a[u][2 * q + 1]; own[4 + q] = bq[u][2 * q] - bq[u][2 * q + 1];
+                }
+                ge::store8<T>(gj + (size_t)i * MRB_CS + cl, g);
+                *reinterpret_cast<unsigned long long*>(ak + (size_t)i * MRB_CS + cl) = pk[u];
+                ge::store8<T>(dx + (p0 + i) * C + c0 + cl, own);          // own term parked in the output (read back below)
+            }
+        }
+    }
+    for (int e = tid; e < N * k; e += MRB_THREADS) atomicAdd(&cnt[(int)idx0[p0 * k + e] + 1], 1);
+    __syncthreads();
+    // ---- exclusive scan of the counts (cnt[j+1] held the count of j): block scan over N + 1 entries
+    {
+        const int per = (N + 1 + MRB_THREADS - 1) / MRB_THREADS;
+        const int lo = tid * per, hi = min(N + 1, lo + per);
+        int s_ = 0;
+        for (int i = lo; i < hi; ++i) s_ += cnt[i];
+        int incl = s_;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t_; }
+        if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
+        int run = base + incl - s_;
+        for (int i = lo; i < hi; ++i) { run += cnt[i]; cnt[i] = run; }        // inclusive prefix: cnt[j] = offset of node j's list end... 
+    }
+    __syncthreads();
+    // after the inclusive scan over the shifted counts, cnt[j] = number of edges into nodes < j  (list of j = [cnt[j], cnt[j+1]))
+    for (int i = tid; i < N; i += MRB_THREADS) fill[i] = cnt[i];
+    __syncthreads();
+    for (int e = tid; e < N * k; e += MRB_THREADS) {
+        const int j = (int)idx0[p0 * k + e];
+        const int pos = atomicAdd(&fill[j], 1);
+        src[pos] = (unsigned short)(e / k);
+        slot[pos] = (unsigned char)(e - (e / k) * k);
+    }
+    __syncthreads();
+    // ---- gather: item = (node j, 8 channels)
+    for (int base = tid; base < total; base += MRB_THREADS * MRB_U) {
+        float o[MRB_U][8];
+#pragma unroll
+        for (int u = 0; u < MRB_U; ++u) {
+            const int e = base + u * MRB_THREADS;
+            if (e < total) {
+                const int j = e / OCT, cl = (e - j * OCT) * 8;
+                ge::load8<T>(dx + (p0 + j) * C + c0 + cl, o[u]);           // own term (this thread wrote it: L2 hit)
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MRB_U; ++u) {
+            const int e = base + u * MRB_THREADS;
+            if (e < total) {
+                const int j = e / OCT, cl = (e - j * OCT) * 8;
+                for (int t_ = cnt[j]; t_ < cnt[j + 1]; ++t_) {
+                    const int i = src[t_];
+                    const unsigned kk = slot[t_];
+                    const unsigned long long pk = *reinterpret_cast<const unsigned long long*>(ak + (size_t)i * MRB_CS + cl);
+                    float g[8];
+                    ge::load8<T>(gj + (size_t)i * MRB_CS + cl, g);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[u][q] += (((pk >> (8 * q)) & 0xffull) == kk) ? g[q] : 0.f;
+                }
+                ge::store8<T>(dx + (p0 + j) * C + c0 + cl, o[u]);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int ge_mrconv_gather_fwd(const float* x, const float* y, const long long* idx_nbr,
@@ -293,5 +414,32 @@ extern "C" int ge_mrconv_gather_nmajor_bwd(const void* dout, const long long* id
         mr_gather_nmajor_bwd_scatter_kernel<__nv_bfloat16><<<(unsigned)ge::cdivll(points, 8), 256, 0, st>>>((const __nv_bfloat16*)dout, idx_nbr, argk, target, C, N, M, k, points);
     }
     GE_CHECK_LAUNCH("ge_mrconv_gather_nmajor_bwd(scatter)");
+    return GE_OK;
+}
+
+// Self-graph backward with the gradient slab resident in shared memory (one launch, dx written once in the activation
+// dtype).  Returns GE_ERR_CAPACITY when the slab does not fit (N * 64 * 4 + N * k * 2 bytes > 220 KB): the caller then
+// takes ge_mrconv_gather_nmajor_bwd.  dx [B,N,C] in `dtype`, overwritten.
+extern "C" int ge_mrconv_gather_nmajor_bwd_self(const void* dout, const long long* idx_nbr, const unsigned char* argk,
+                                                void* dx, int dtype, int B, int C, int N, int k, ge_stream_t stream) {
+    GE_REQUIRE(dout && idx_nbr && argk && dx, GE_ERR_ARG, "ge_mrconv_gather_nmajor_bwd_self: null pointer");
+    GE_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, GE_ERR_ARG, "ge_mrconv_gather_nmajor_bwd_self: bad dimension");
+    GE_REQUIRE(k <= 32 && C % MRB_CS == 0 && N <= 65535 && B <= 65535, GE_ERR_SHAPE,
+               "ge_mrconv_gather_nmajor_bwd_self: needs k <= 32, C %% 32 == 0, N <= 65535");
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_mrconv_gather_nmajor_bwd_self: unsupported dtype %d", dtype);
+    const size_t es_ = dtype == GE_DTYPE_F32 ? 4 : 2;
+    const size_t smem = (size_t)N * MRB_CS * (es_ + 1) + (size_t)(2 * N + 1) * sizeof(int) + (size_t)N * k * 3 + 16;
+    GE_REQUIRE(smem <= 110 * 1024, GE_ERR_CAPACITY, "ge_mrconv_gather_nmajor_bwd_self: N=%d does not fit shared memory", N);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(C / MRB_CS, B);
+    static size_t c0 = 0, c1 = 0;
+    if (dtype == GE_DTYPE_F32) {
+        if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(mr_gather_nmajor_bwd_self_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_mrconv_gather_nmajor_bwd_self(attr)"); c0 = smem; }
+        mr_gather_nmajor_bwd_self_kernel<float><<<grid, MRB_THREADS, smem, st>>>((const float*)dout, idx_nbr, argk, (float*)dx, C, N, k);
+    } else {
+        if (smem > c1) { GE_CUDA(cudaFuncSetAttribute(mr_gather_nmajor_bwd_self_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_mrconv_gather_nmajor_bwd_self(attr)"); c1 = smem; }
+        mr_gather_nmajor_bwd_self_kernel<__nv_bfloat16><<<grid, MRB_THREADS, smem, st>>>((const __nv_bfloat16*)dout, idx_nbr, argk, (__nv_bfloat16*)dx, C, N, k);
+    }
+    GE_CHECK_LAUNCH("ge_mrconv_gather_nmajor_bwd_self");
     return GE_OK;
 }

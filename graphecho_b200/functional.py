@@ -301,6 +301,12 @@ class _MRGatherNMajor(Function):
         i0, argk = ctx.saved_tensors
         B, C, N, M, k, has_y, dt = ctx.cfg
         d = dout.to(dt).contiguous()
+        es = d.element_size()
+        if not has_y and C % 32 == 0 and N * 32 * (es + 1) + (2 * N + 1) * 4 + N * k * 3 + 16 <= 110 * 1024 and N <= 65535 and B <= 65535:
+            dxs = torch.empty((B, N, C), device=d.device, dtype=dt)
+            call("ge_mrconv_gather_nmajor_bwd_self", ptr(d), ptr(i0), ptr(argk), ptr(dxs), _dtype_code(d), B, C, N, k, stream(),
+                 work=((2 * es + 1 + es) * B * C * N + 8 * B * N * k, 2 * B * C * N))       # dout, argk in; dx out
+            return dxs, None, None
         dx = torch.empty((B, N, C), device=d.device, dtype=torch.float32)
         dy = torch.zeros((B, M, C), device=d.device, dtype=torch.float32) if has_y else None
         es = d.element_size()

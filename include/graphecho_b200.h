@@ -133,6 +133,10 @@ int ge_mrconv_gather_nmajor_fwd(const void* x, const void* y, const long long* i
 int ge_mrconv_gather_nmajor_bwd(const void* dout, const long long* idx_nbr, const unsigned char* argk,
                                 float* dx, float* dy, int dtype, int B, int C, int N, int M, int k,
                                 ge_stream_t stream);
+/* Self-graph (y == NULL) backward with the gradient slab [N][64 channels] resident in shared memory: one launch, dx
+ * [B,N,C] written once in `dtype`.  GE_ERR_CAPACITY when N * 256 + N * k * 2 bytes exceed 220 KB (use the entry above). */
+int ge_mrconv_gather_nmajor_bwd_self(const void* dout, const long long* idx_nbr, const unsigned char* argk,
+                                     void* dx, int dtype, int B, int C, int N, int k, ge_stream_t stream);
 
 /* ---- K6: TGCN pyramid pooling + concat ------------------------------------------------------
  * avg_pool2d(r) per level + channel concat of TGCN.DyGraphConv2d.forward (models/TGCN.py:62-70),
