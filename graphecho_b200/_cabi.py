@@ -28,6 +28,7 @@ _SIGNATURES = {
     "ge_affinity_pairwise_fwd": (c_int, [P, P, P, P, P, I, I, I, I, P]),
     "ge_affinity_pairwise_bwd_workspace_bytes": (c_size_t, [I, I, I, I]),
     "ge_affinity_pairwise_bwd": (c_int, [P, P, P, P, P, P, P, P, P, Z, I, I, I, I, P]),
+    "ge_sinkhorn_rpm_set_path": (c_int, [I]),
     "ge_sinkhorn_rpm_cluster_size": (c_int, [I, I, I]),
     "ge_sinkhorn_rpm_fwd": (c_int, [P, P, P, P, P, I, I, I, I, I, I, P]),
     "ge_sinkhorn_rpm_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, P]),

@@ -20,6 +20,7 @@
 // the saved potentials, recomputing the softmax weights exp(z - r_t - c_t) on the fly.
 #include "common.cuh"
 #include "../../include/graphecho_b200.h"
+#include "sinkhorn_rpm_reg.h"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -84,10 +85,12 @@ __device__ __forceinline__ void cluster_sum4(cg::cluster_group& cl, float* xchg,
 __global__ void __launch_bounds__(RPM_THREADS, 1)
 sinkhorn_rpm_fwd_kernel(const float* __restrict__ M, float* __restrict__ P,
                         float* __restrict__ hist_r, float* __restrict__ hist_c,
-                        float* __restrict__ stats, int N1, int N2, int n_iters, int apply_instnorm) {
+                        float* __restrict__ stats, int N1, int N2, int n_iters, int apply_instnorm, int gate) {
     cg::cluster_group cl = cg::this_cluster();
     const unsigned cs = cl.num_blocks(), rank = cl.block_rank();
     const int prob = blockIdx.x / cs;
+    // gate: run only the problems the register-resident kernel left to this one (stats[2] == 1)
+    if (gate && stats[(size_t)prob * 4 + 2] == 0.f) return;
     const int R = ge::cdiv(N1, (int)cs);
     const int row0 = rank * R;
     const int rows = max(0, min(R, N1 - row0));
@@ -133,7 +136,7 @@ sinkhorn_rpm_fwd_kernel(const float* __restrict__ M, float* __restrict__ P,
             s.z[i * ld + j] = (s.z[i * ld + j] - mean) * rstd;
         }
     }
-    if (rank == 0 && tid == 0) { stats[0] = mean; stats[1] = rstd; stats[2] = 0.f; stats[3] = 0.f; }
+    if (rank == 0 && tid == 0) { stats[0] = mean; stats[1] = rstd; stats[2] = 1.f; stats[3] = 0.f; }   // 1: log-domain history
     for (int j = tid; j < N2p; j += RPM_THREADS) s.c[j] = 0.f;
     for (int i = tid; i < R; i += RPM_THREADS) s.r[i] = 0.f;
     __syncthreads();
@@ -204,10 +207,11 @@ __global__ void __launch_bounds__(RPM_THREADS, 1)
 sinkhorn_rpm_bwd_kernel(const float* __restrict__ M, const float* __restrict__ G,
                         const float* __restrict__ hist_r, const float* __restrict__ hist_c,
                         const float* __restrict__ stats, float* __restrict__ dM,
-                        int N1, int N2, int n_iters, int apply_instnorm) {
+                        int N1, int N2, int n_iters, int apply_instnorm, int gate) {
     cg::cluster_group cl = cg::this_cluster();
     const unsigned cs = cl.num_blocks(), rank = cl.block_rank();
     const int prob = blockIdx.x / cs;
+    if (gate && stats[(size_t)prob * 4 + 2] == 0.f) return;
     const int R = ge::cdiv(N1, (int)cs);
     const int row0 = rank * R;
     const int rows = max(0, min(R, N1 - row0));
@@ -408,9 +412,25 @@ int launch_cluster(K kernel, const char* name, int cs, int batch, size_t smem, c
 
 }  // namespace
 
+// 0 = automatic, 1 = log-domain (shared-memory) kernels only, 2 / 3 = register path with 4 / 8 rows per thread
+static int g_rpm_path = 0;
+
+extern "C" int ge_sinkhorn_rpm_set_path(int path) {
+    GE_REQUIRE(path >= 0 && path <= 3, GE_ERR_ARG, "ge_sinkhorn_rpm_set_path: path must be 0..3 (got %d)", path);
+    g_rpm_path = path;
+    return GE_OK;
+}
+
 extern "C" int ge_sinkhorn_rpm_cluster_size(int N1, int N2, int backward) {
     if (N1 <= 0 || N2 <= 0) return -1;
     return pick_cluster(N1, N2, backward != 0, 0);
+}
+
+// cluster_size > 0 requests the log-domain kernel with that cluster size; 0 takes the register-resident
+// exponent-domain kernel when the problem fits it (sinkhorn_rpm_reg.cu) and runs the log-domain kernel
+// behind it, gated per problem on the flag the first kernel leaves in stats[2] (max z too large).
+static bool use_reg_path(int N1, int N2, int n_iters, int cluster_size) {
+    return cluster_size == 0 && g_rpm_path != 1 && ge::rpmreg::fits(N1, N2, n_iters);
 }
 
 extern "C" int ge_sinkhorn_rpm_fwd(const float* M, float* P, float* hist_r, float* hist_c, float* stats,
@@ -423,8 +443,16 @@ extern "C" int ge_sinkhorn_rpm_fwd(const float* M, float* P, float* hist_r, floa
                "ge_sinkhorn_rpm_fwd: %dx%d does not fit the on-chip cluster layout (cluster_size=%d)", N1, N2, cluster_size);
     const int ld = (N2 + 3) & ~3;
     const size_t smem = rpm_smem_floats(ge::cdiv(N1, cs), ld, ld, false) * sizeof(float);
+    const bool reg = use_reg_path(N1, N2, n_iters, cluster_size);
+    if (reg) {
+        // 8 rows per thread (half the CTAs per problem) once the batch fills the machine anyway
+        const int tr = g_rpm_path == 2 ? 4 : g_rpm_path == 3 ? 8 : ((long long)batch * ge::cdiv(N1, 64) >= 4LL * ge::sm_count() ? 8 : 4);
+        const int rc = ge::rpmreg::fwd(M, P, hist_r, hist_c, stats, batch, N1, N2, n_iters, apply_instnorm, tr,
+                                       (cudaStream_t)stream);
+        if (rc != GE_OK) return rc;
+    }
     return launch_cluster(sinkhorn_rpm_fwd_kernel, "ge_sinkhorn_rpm_fwd", cs, batch, smem, (cudaStream_t)stream,
-                          M, P, hist_r, hist_c, stats, N1, N2, n_iters, apply_instnorm);
+                          M, P, hist_r, hist_c, stats, N1, N2, n_iters, apply_instnorm, reg ? 1 : 0);
 }
 
 extern "C" int ge_sinkhorn_rpm_bwd(const float* M, const float* G, const float* hist_r, const float* hist_c,
@@ -437,6 +465,12 @@ extern "C" int ge_sinkhorn_rpm_bwd(const float* M, const float* G, const float* 
                "ge_sinkhorn_rpm_bwd: %dx%d does not fit the on-chip cluster layout (cluster_size=%d)", N1, N2, cluster_size);
     const int ld = (N2 + 3) & ~3;
     const size_t smem = rpm_smem_floats(ge::cdiv(N1, cs), ld, ld, true) * sizeof(float);
+    const bool reg = use_reg_path(N1, N2, n_iters, cluster_size);
+    if (reg) {
+        const int rc = ge::rpmreg::bwd(M, G, hist_r, hist_c, stats, dM, batch, N1, N2, n_iters, apply_instnorm,
+                                       (cudaStream_t)stream);
+        if (rc != GE_OK) return rc;
+    }
     return launch_cluster(sinkhorn_rpm_bwd_kernel, "ge_sinkhorn_rpm_bwd", cs, batch, smem, (cudaStream_t)stream,
-                          M, G, hist_r, hist_c, stats, dM, N1, N2, n_iters, apply_instnorm);
+                          M, G, hist_r, hist_c, stats, dM, N1, N2, n_iters, apply_instnorm, reg ? 1 : 0);
 }

@@ -55,12 +55,18 @@ int ge_affinity_pairwise_bwd(const float* A, const float* B, const float* w2, co
 
 /* ---- K4: instance-norm + slack Sinkhorn + exp --------------------------------------------
  * P = exp(sinkhorn_rpm(InstanceNorm2d(1)(M), n_iters, slack=True))
- * (models/graph_matching.py:574-575 and 637-676).  One thread-block cluster per problem,
- * matrix resident in (distributed) shared memory for the whole loop.
- * M, P [batch,N1,N2]; hist_r [batch,n_iters,N1], hist_c [batch,n_iters,N2] receive the row /
- * column log-potentials after every pass (saved for the backward); stats [batch,4] receives
- * (mean, rstd, -, -).  apply_instnorm=0 skips the normalisation (plain sinkhorn_rpm).
- * cluster_size: 0 = choose, else 1/2/4/8/16.  GE_ERR_CAPACITY if N1*N2 does not fit. */
+ * (models/graph_matching.py:574-575 and 637-676).  One thread-block cluster per problem, matrix on chip for the
+ * whole loop.  Two kernels behind one entry point:
+ *  - register-resident, exponent domain (K = exp(z) in a per-thread register tile, u = exp(-r), v = exp(-c); two
+ *    matrix-vector products per iteration, no exp/log in the loop) for N2 <= 256, N1 <= 512;
+ *  - log domain with the matrix in (distributed) shared memory for everything else, for cluster_size > 0, and --
+ *    gated per problem on stats[2] -- for inputs whose max z (> 80) would overflow the exponent domain.
+ * M, P [batch,N1,N2]; hist_r [batch,n_iters,N1], hist_c [batch,n_iters,N2] receive the row / column potentials after
+ * every pass, saved for the backward (u_t, v_t when stats[2] == 0, log-potentials r_t, c_t when stats[2] == 1);
+ * stats [batch,4] receives (mean, rstd, path, -).  apply_instnorm=0 skips the normalisation (plain sinkhorn_rpm).
+ * cluster_size: 0 = choose, else 1/2/4/8/16 (log-domain kernel).  GE_ERR_CAPACITY if N1*N2 does not fit.
+ * ge_sinkhorn_rpm_set_path: 0 automatic, 1 log-domain only, 2 / 3 register path with 4 / 8 rows per thread (tuning). */
+int ge_sinkhorn_rpm_set_path(int path);
 int ge_sinkhorn_rpm_cluster_size(int N1, int N2, int backward);
 int ge_sinkhorn_rpm_fwd(const float* M, float* P, float* hist_r, float* hist_c, float* stats,
                         int batch, int N1, int N2, int n_iters, int apply_instnorm,

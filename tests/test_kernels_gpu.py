@@ -82,6 +82,53 @@ def test_sinkhorn_rpm_fwd_bwd_vs_oracle(dev, n1, n2, cs):
     close(Md.grad, Mo.grad, rtol=5e-3, atol=2e-6)
 
 
+@pytest.mark.parametrize("path", [1, 2, 3])
+@pytest.mark.parametrize("n1,n2,iters,instnorm", [(252, 252, 20, True), (250, 251, 20, True), (37, 45, 20, True),
+                                                  (129, 128, 7, True), (511, 130, 20, True), (64, 256, 3, False),
+                                                  (5, 3, 20, True), (300, 77, 0, True)])
+def test_sinkhorn_rpm_register_path_vs_oracle(dev, path, n1, n2, iters, instnorm):
+    """The register-resident exponent-domain kernels (4 and 8 rows per thread) and the log-domain kernel against the
+    oracle's literal log-domain loop (graph_matching.py:637-676), forward and gradient, batched (2 problems)."""
+    from graphecho_b200 import _cabi
+    torch.manual_seed(n1 * 3 + n2 + iters)
+    M = torch.randn(2, n1, n2) * 1.3 + 0.2
+    W = torch.randn(2, n1, n2)
+    Mo = M.clone().requires_grad_()
+    if instnorm:
+        Po = torch.stack([G.sinkhorn_rpm_exp(Mo[b], iters, True) for b in range(2)])
+    else:
+        Po = G.sinkhorn_rpm(Mo, iters, True).exp()
+    (Po * W).sum().backward()
+    _cabi.lib().ge_sinkhorn_rpm_set_path(path)
+    try:
+        Md = M.to(dev).requires_grad_()
+        Pd = GF.sinkhorn_rpm_exp(Md, iters, instnorm)
+        (Pd * W.to(dev)).sum().backward()
+    finally:
+        _cabi.lib().ge_sinkhorn_rpm_set_path(0)
+    close(Pd, Po, rtol=5e-4, atol=1e-6)
+    close(Md.grad, Mo.grad, rtol=5e-3, atol=2e-6)
+
+
+def test_sinkhorn_rpm_mixed_batch_defers_only_the_outlier_problem(dev):
+    """Batch of 3 where problem 1 has an instance-normed entry ~ 100: that problem takes the log-domain kernel
+    (stats[2] == 1), the others stay on the register path; all three match the oracle, forward and gradient."""
+    torch.manual_seed(5)
+    M = torch.randn(3, 100, 120) * 0.5
+    M[1] *= 0.02
+    M[1, 3, 5] = 500.0
+    W = torch.randn(3, 100, 120)
+    Mo = M.clone().requires_grad_()
+    Po = torch.stack([G.sinkhorn_rpm_exp(Mo[b], 20, True) for b in range(3)])
+    (Po * W).sum().backward()
+    Md = M.to(dev).requires_grad_()
+    Pd = GF.sinkhorn_rpm_exp(Md, 20, True)
+    (Pd * W.to(dev)).sum().backward()
+    assert torch.isfinite(Pd).all() and torch.isfinite(Md.grad).all()
+    close(Pd, Po, rtol=1e-3, atol=1e-6)
+    close(Md.grad, Mo.grad, rtol=5e-3, atol=2e-6)
+
+
 @pytest.mark.parametrize("iters", [0, 1, 5])
 def test_sinkhorn_rpm_plain_and_batched(dev, iters, golden):
     torch.manual_seed(iters)
