@@ -305,26 +305,34 @@ def north_star_rooflines(dev, peaks):
     w2, b2 = torch.randn(512, device=dev), torch.randn(1, device=dev)
     for batch, n in ((1, 252), (512, 252)):
         A, B = torch.randn(batch, n, 512, device=dev), torch.randn(batch, n, 512, device=dev)
+        # K3 is instruction-issue bound (no GEMM in it: the ReLU couples i, j and k).  "fp32" rows count fp32 pipe
+        # operations against SMs x 128 lanes x 2 x clock, i.e. an FFMA counts 2 and a max / gated add counts 1:
+        # forward = max + fma per term (3 ops, 2 issue slots), backward = gate + 2 gated adds per term (3 ops, 3 slots).
+        # `issue_frac` is the same time against the issue-slot bound itself (SMs x 128 lanes x clock).
+        issue = ffma / 2
         ms = _timed_kernel(lambda: GF.affinity_pairwise(A, B, w2, b2), flush)
-        add("ge_affinity_pairwise_fwd", f"{batch}x{n}x{n}x512", ms, 4 * batch * (512 * 2 * n + n * n), 3 * batch * 512 * n * n, "fp32")
+        add("ge_affinity_pairwise_fwd", f"{batch}x{n}x{n}x512", ms, 4 * batch * (512 * 2 * n + n * n), 3 * batch * 512 * n * n, "fp32",
+            {"issue_frac": round(2 * batch * 512 * n * n / ms / 1e6 / issue, 4)})
         Ar, Br = A.clone().requires_grad_(), B.clone().requires_grad_()
         Mx = GF.affinity_pairwise(Ar, Br, w2, b2)
         g = torch.randn_like(Mx)
         ms = _timed_kernel(lambda: torch.autograd.grad(Mx, (Ar, Br), g, retain_graph=True), flush)
-        add("ge_affinity_pairwise_bwd", f"{batch}x{n}x{n}x512", ms, 4 * batch * (512 * 4 * n + 2 * n * n), 8 * batch * 512 * n * n, "fp32")
+        add("ge_affinity_pairwise_bwd", f"{batch}x{n}x{n}x512", ms, 4 * batch * (512 * 4 * n + 2 * n * n), 3 * batch * 512 * n * n, "fp32",
+            {"issue_frac": round(3 * batch * 512 * n * n / ms / 1e6 / issue, 4)})
         M = torch.randn(batch, n, n, device=dev)
         ms = _timed_kernel(lambda: GF.sinkhorn_rpm_exp(M, 20, True), flush)
-        # 8 N1 N2 bytes for the whole loop (section 8(d) K4); the loop itself is on-chip: the binding unit is the MUFU
-        # (2 ex2 per element per iteration) -- reported beside the HBM figure
-        mufu_peak = _cabi.lib().ge_device_sm_count() * 16 * (peaks.get("sm_max_mhz") or 1965.0) * 1e6      # ex2/s
-        add("ge_sinkhorn_rpm_fwd(instnorm+20it+exp)", f"{batch}x{n}x{n}", ms, 8 * batch * n * n, batch * n * n * 166, "hbm",
+        # 8 N1 N2 bytes for the whole loop (section 8(d) K4).  The loop itself is on-chip; in the exponent domain it is
+        # 2 matrix-vector products per iteration = 4 N1 N2 flops per iteration on the fp32 pipe (`fp32_frac`); what
+        # actually bounds it is the per-iteration dependency chain (reduce -> exchange -> reciprocal), see DESIGN.md
+        add("ge_sinkhorn_rpm_fwd(instnorm+20it+exp)", f"{batch}x{n}x{n}", ms, 8 * batch * n * n, batch * n * n * (4 * 20 + 12), "hbm",
             {"sinkhorn_iters_per_s": round(20 * batch / (ms / 1e3)),
-             "mufu_frac": round(batch * n * n * 41 / (ms / 1e3) / mufu_peak, 4)})
+             "fp32_frac": round(batch * n * n * (4 * 20 + 12) / ms / 1e6 / ffma, 4)})
         Mr = M.clone().requires_grad_()
         Pm = GF.sinkhorn_rpm_exp(Mr, 20, True)
         g = torch.randn_like(Pm)
         ms = _timed_kernel(lambda: torch.autograd.grad(Pm, Mr, g, retain_graph=True), flush)
-        add("ge_sinkhorn_rpm_bwd", f"{batch}x{n}x{n}", ms, 12 * batch * n * n, batch * n * n * 250, "hbm")
+        add("ge_sinkhorn_rpm_bwd", f"{batch}x{n}x{n}", ms, 12 * batch * n * n, batch * n * n * (8 * 20 + 16), "hbm",
+            {"fp32_frac": round(batch * n * n * (8 * 20 + 16) / ms / 1e6 / ffma, 4)})
     Bf, C, N, k = 256, 256, 784, 9
     xn = torch.randn(Bf, N, C, device=dev).bfloat16()
     ms = _timed_kernel(lambda: GF.knn_graph_nmajor(xn, None, k, 1), flush, iters=10)

@@ -283,7 +283,7 @@ rpm_reg_fwd_kernel(const float* __restrict__ M, float* __restrict__ P, float* __
         }
         int row;
         const float tot = lane_transpose_reduce<TR>(p, lane, row);
-        const float uval = 1.f / (1.f + tot);
+        const float uval = __frcp_rn(1.f + tot);
         if ((lane & (32 / TR - 1)) == 0) {
             s_u[warp * TR + row] = uval;
             if (row < rpw && grow0 + row < rows_end) hist_u[(size_t)t * N1 + grow0 + row] = uval;
@@ -302,7 +302,7 @@ rpm_reg_fwd_kernel(const float* __restrict__ M, float* __restrict__ P, float* __
         }
         const float ctot = column_reduce<QC>(cl, cs, q, s_part, s_x, cpar);
         if (tid < NC) {
-            const float vval = 1.f / (1.f + ctot);
+            const float vval = __frcp_rn(1.f + ctot);
             s_v[tid] = vval;
             if (rank == 0 && tid < N2) hist_v[(size_t)t * N2 + tid] = vval;
         }

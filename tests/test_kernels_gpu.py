@@ -64,6 +64,30 @@ def test_affinity_pairwise_batched(dev):
     close(M, ref, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("batch,n1,n2,H", [(128, 70, 90, 64), (3, 70, 90, 96), (1, 252, 250, 512), (40, 33, 64, 288)])
+def test_affinity_pairwise_backward_both_modes(dev, batch, n1, n2, H):
+    """dA, dB, dw2, db2 against autograd through the literal relu-coupled sum: the split-Q partial mode (small
+    batches: one fused sweep for both sides) and the direct mode (one sweep per side once the row tiles fill the
+    machine), incl. a hidden width above one 256-channel pass of the forward."""
+    torch.manual_seed(batch + n1)
+    A = torch.randn(batch, n1, H, device=dev).requires_grad_()
+    B = torch.randn(batch, n2, H, device=dev).requires_grad_()
+    w2 = (torch.randn(H, device=dev) * 0.05).requires_grad_()
+    b2 = torch.randn(1, device=dev).requires_grad_()
+    Gm = torch.randn(batch, n1, n2, device=dev)
+    M = GF.affinity_pairwise(A, B, w2, b2)
+    got = torch.autograd.grad(M, (A, B, w2, b2), Gm)
+    ref = torch.zeros(batch, n1, n2, device=dev)
+    for k0 in range(0, H, 32):      # chunked over the hidden axis to bound the [b, n1, n2, 32] intermediate
+        ref = ref + (torch.relu(A[:, :, None, k0:k0 + 32] + B[:, None, :, k0:k0 + 32]) * w2[k0:k0 + 32]).sum(-1)
+    ref = ref + b2
+    close(M, ref, rtol=1e-4, atol=1e-4)
+    want = torch.autograd.grad(ref, (A, B, w2, b2), Gm)
+    for g_, w_, name in zip(got, want, ("dA", "dB", "dw2", "db2")):
+        scale = float(w_.abs().max())
+        assert torch.allclose(g_, w_, rtol=2e-3, atol=2e-5 * max(scale, 1.0)), (name, float((g_ - w_).abs().max()), scale)
+
+
 # ---------------------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("n1,n2,cs", [(37, 45, 0), (6, 6, 0), (1, 9, 0), (250, 251, 0), (320, 204, 0),
                                       (100, 100, 1), (100, 100, 2), (100, 100, 4), (100, 101, 8), (130, 97, 16),
