@@ -73,6 +73,8 @@ _SIGNATURES = {
     "ge_seg_loss_bwd": (c_int, [P, P, P, P, P, I, I, I, P]),
     "ge_mask_boxes": (c_int, [P, P, I, I, I, I, I, P]),
     "ge_sampler_labels": (c_int, [P, P, P, P, P, P, P, P, I, I, I, P]),
+    "ge_sampler_gather": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "ge_sampler_scatter": (c_int, [P, P, P, P, P, P, P, I, I, I, P]),
     "ge_spectral_bipartition_max_points": (c_int, []),
     "ge_spectral_bipartition": (c_int, [P, P, I, I, I, I, P]),
     "ge_seg_tail_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P]),

@@ -241,8 +241,8 @@ affinity_pairwise_bwd_kernel(const float* __restrict__ P, const float* __restric
     }
 }
 
-// Partial mode: sums the per-CTA partials of 8 rows of [A ; B] per CTA, scales by w, and forms the dw partial.
-constexpr int FR = 8;
+// Partial mode: sums the per-CTA partials of FR rows of [A ; B] per CTA, scales by w, and forms the dw partial.
+constexpr int FR = 2;
 __global__ void __launch_bounds__(512)
 affinity_bwd_rows_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ w2,
                          const float* __restrict__ dA_part, const float* __restrict__ dB_part,
@@ -257,14 +257,16 @@ affinity_bwd_rows_kernel(const float* __restrict__ A, const float* __restrict__ 
             const int row = blockIdx.x * FR + rr;
             if (row < N1) {
                 float s = 0.f;
-                for (int p = 0; p < n_js; ++p) s += dA_part[(((size_t)b * n_js + p) * N1 + row) * H + k];
+#pragma unroll 8
+                for (int p = 0; p < n_js; ++p) s += __ldg(dA_part + (((size_t)b * n_js + p) * N1 + row) * H + k);
                 const size_t o = ((size_t)b * N1 + row) * H + k;
                 dA[o] = wk * s;
                 accW = fmaf(__ldg(A + o), s, accW);
             } else if (row - N1 < N2) {
                 const int j = row - N1;
                 float s = 0.f;
-                for (int p = 0; p < n_it; ++p) s += dB_part[(((size_t)b * n_it + p) * N2 + j) * H + k];
+#pragma unroll 8
+                for (int p = 0; p < n_it; ++p) s += __ldg(dB_part + (((size_t)b * n_it + p) * N2 + j) * H + k);
                 const size_t o = ((size_t)b * N2 + j) * H + k;
                 dB[o] = wk * s;
                 accW = fmaf(__ldg(B + o), s, accW);

@@ -918,6 +918,100 @@ def sampler_labels(boxes, level_hw, strides, size_ranges):
     return out, counts
 
 
+def sampler_gather_plan(counts, num_nodes_per_class=100, bg_ratio=8, sample_bg_nodes=True):
+    """Host half of the picks (graph_matching.py:984-1003) for one domain from its per-level (n_pos, n_neg) counts:
+    per level (n_neg_all, step, n_pos_pick, n_neg_pick, neg_all, out_pos, out_neg) and the node count."""
+    rows = []
+    for n_pos_all, n_neg_all in counts:
+        n_pos_all, n_neg_all = int(n_pos_all), int(n_neg_all)
+        step = max(n_pos_all // num_nodes_per_class, 1)
+        n_pos_pick = -(-n_pos_all // step) if step > 1 else n_pos_all
+        if not sample_bg_nodes:
+            neg_all, n_neg_pick = 0, 0
+        elif n_pos_all > n_neg_all:
+            neg_all, n_neg_pick = 1, n_neg_all
+        else:
+            neg_all, n_neg_pick = 0, n_pos_pick // bg_ratio
+        rows.append([n_neg_all, step, n_pos_pick, n_neg_pick, neg_all, 0, 0])
+    total_neg = sum(r[3] for r in rows)
+    on, op = 0, total_neg
+    for r in rows:
+        r[5], r[6] = op, on
+        op += r[2]
+        on += r[3]
+    return rows, op
+
+
+class _SamplerGather(Function):
+    """Nodes of every domain in one launch: forward(plan, *feats) -> (nodes_0, labels_0, nodes_1, labels_1, ...).
+    plan = [(per-level label views, per-level feat index into feats, batch_offset, rows, n_nodes), ...] per domain."""
+
+    @staticmethod
+    def forward(ctx, plan, *feats):
+        import ctypes
+        _need_cuda(*feats)
+        fv = [_nhwc_view(f) for f in feats]
+        dt = _dtype_code(fv[0])
+        C = fv[0].shape[1]
+        dev = fv[0].device
+        outs, ent = [], []
+        for labels, fidx, boff, rows, n_nodes in plan:
+            nodes = torch.empty((n_nodes, C), device=dev, dtype=torch.float32)
+            nlab = torch.empty(n_nodes, device=dev, dtype=torch.int64)
+            src = torch.empty(n_nodes, device=dev, dtype=torch.int64)
+            outs += [nodes, nlab]
+            for lab, fi, r in zip(labels, fidx, rows):
+                f = fv[fi]
+                if f.shape[1] != C or _dtype_code(f) != dt:
+                    raise _cabi.GraphEchoNativeError("sampler_gather: all feature levels must share C and dtype")
+                hw = f.shape[2] * f.shape[3]
+                ent.append((f, lab, nodes, nlab, src, lab.numel(), boff * hw, r, fi))
+        n = len(ent)
+        PA, LA, IA = ctypes.c_void_p * n, ctypes.c_longlong * n, ctypes.c_int * n
+        col = lambda k: IA(*[int(e[7][k]) for e in ent])
+        call("ge_sampler_gather", PA(*[e[0].data_ptr() for e in ent]), PA(*[e[1].data_ptr() for e in ent]),
+             PA(*[e[2].data_ptr() for e in ent]), PA(*[e[3].data_ptr() for e in ent]), PA(*[e[4].data_ptr() for e in ent]),
+             LA(*[int(e[5]) for e in ent]), LA(*[int(e[6]) for e in ent]), col(0), col(1), col(2), col(3), col(4), col(5), col(6),
+             n, C, dt, stream(),
+             work=(8 * sum(int(e[5]) for e in ent) + sum(o.numel() * 4 for o in outs[::2]) * 2, 0))
+        ctx.ent = [(e[4], e[7], e[8]) for e in ent]
+        ctx.meta = (C, dt, [tuple(f.shape) for f in fv], [f.dtype for f in fv], dev,
+                    [len(p[0]) for p in plan])
+        ctx.mark_non_differentiable(*outs[1::2])
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        import ctypes
+        C, dt, shapes, dtypes, dev, per_domain = ctx.meta
+        dn = [_f32c(g) if g is not None else None for g in grads[0::2]]
+        need = ctx.needs_input_grad[1:]
+        dfeat = [torch.zeros(sh, device=dev, dtype=d_).contiguous(memory_format=torch.channels_last) if nd else None
+                 for sh, d_, nd in zip(shapes, dtypes, need)]
+        ent, k = [], 0
+        for d, nlev in enumerate(per_domain):
+            for _ in range(nlev):
+                src, r, fi = ctx.ent[k]
+                k += 1
+                if dfeat[fi] is not None and dn[d] is not None and (r[2] + r[3]) > 0:
+                    ent.append((dfeat[fi], dn[d], src, r))
+        if ent:
+            n = len(ent)
+            PA, IA = ctypes.c_void_p * n, ctypes.c_int * n
+            col = lambda k_: IA(*[int(e[3][k_]) for e in ent])
+            call("ge_sampler_scatter", PA(*[e[0].data_ptr() for e in ent]), PA(*[e[1].data_ptr() for e in ent]),
+                 PA(*[e[2].data_ptr() for e in ent]), col(2), col(3), col(5), col(6), n, C, dt, stream(),
+                 work=(sum((e[3][2] + e[3][3]) * C * 6 for e in ent), 0))
+        return (None, *dfeat)
+
+
+def sampler_gather(plan, feats):
+    """See _SamplerGather.  Returns [(nodes fp32 [n,C], labels int64 [n]) per domain]."""
+    out = _SamplerGather.apply(plan, *feats)
+    return [(out[2 * i], out[2 * i + 1]) for i in range(len(plan))]
+
+
 class _GradReverse(Function):
     """Gradient reversal (gradient_reversal.py:6-24) without the reference's full clone()."""
 

@@ -184,8 +184,8 @@ class GModule(nn.Module):
             plan_s = gen.plan(self.compute_locations(feat_s), self.find_bbox(targets), geo, self.fpn_strides)
             labels_s = plan_s[0]
             counts_s, counts_t = torch.stack([plan_s[1], plan_t[1]]).tolist()       # ONE host sync for both domains
-        nodes_1, labels_1, weights_1 = gen.gather(feat_s, labels_s, counts_s, off_s)
-        nodes_2, labels_2, weights_2 = gen.gather(feat_t, plan_t[0], counts_t, off_t)
+        (nodes_1, labels_1, weights_1), (nodes_2, labels_2, weights_2) = gen.gather_pair(
+            (feat_s, labels_s, counts_s, off_s), (feat_t, plan_t[0], counts_t, off_t))
         if nodes_1.size(0) < 6 or nodes_1.dim() == 1:                             # graph_matching.py:259-260
             return features, (nodes_1, nodes_2), losses
         nodes_1, nodes_2 = nodes_1.float(), nodes_2.float()
@@ -549,6 +549,31 @@ class PrototypeComputation(object):
             pos_pts = torch.cat([neg_pts, pos_pts], dim=0)
             pos_lab = torch.cat([pos_lab.new_zeros(neg_pts.size(0)), pos_lab])
         return pos_pts, pos_lab, torch.ones_like(pos_lab).long()
+
+    def gather_pair(self, *domains):
+        """`gather` for several domains (features, labels, counts, batch_offset) at once.  CUDA NHWC feature maps take
+        ONE kernel launch for every level of every domain (ge_sampler_gather; its backward is one scatter launch, with
+        one gradient tensor per feature map even when the domains share the maps); anything else the torch route."""
+        f0 = domains[0][0][0]
+        fused = (f0.is_cuda and all(f.is_cuda and f.dim() == 4 and f.dtype == f0.dtype and f.size(1) == f0.size(1)
+                                    for d in domains for f in d[0])
+                 and f0.dtype in (torch.float32, torch.bfloat16) and f0.size(1) % 4 == 0
+                 and sum(len(d[1]) for d in domains) <= 10)
+        if not fused:
+            return [self.gather(*d) for d in domains]
+        feats, plan = [], []
+        for features, labels, counts, boff in domains:
+            fidx = []
+            for f in features[:len(labels)]:
+                k = next((i for i, g in enumerate(feats) if g is f), None)
+                if k is None:
+                    feats.append(f)
+                    k = len(feats) - 1
+                fidx.append(k)
+            rows, n_nodes = GF.sampler_gather_plan(counts, self.num_nodes_per_class, self.bg_ratio, self.sample_bg_nodes)
+            plan.append((list(labels), fidx, int(boff), rows, n_nodes))
+        out = GF.sampler_gather(plan, feats)
+        return [(n, l, torch.ones_like(l)) for n, l in out]
 
     def __call__(self, locations, features, targets):
         if not locations:

@@ -309,6 +309,25 @@ int ge_sampler_labels(const float* boxes, long long* labels, int* counts, const 
                       const int* strides, const float* size_lo, const float* size_hi, int levels, int B, int K,
                       ge_stream_t stream);
 
+/* f1, second half (models/graph_matching.py:978-1013): positive / negative picks of every level and the row gather of
+ * the picked locations, ONE launch for up to 10 (domain, level) entries; ge_sampler_scatter is its backward.
+ * Per entry: feats = NHWC feature map of the level [images,h,w,C] in `dtype`; labels int64 [n_loc] from
+ * ge_sampler_labels; shift = batch_offset*h*w (row of the first labelled image in feats); n_neg_all = #labels == 0;
+ * step = positive stride (n_pos_all // 100, >= 1); n_pos_pick / n_neg_pick = nodes kept; neg_all = 1 keeps every negative
+ * (more positives than negatives), else the negatives of rank floor(linspace(0, n_neg_all-2, n_neg_pick)) (fp64, as
+ * numpy); out_pos / out_neg = first slot of the level's positives / negatives in the domain's arrays nodes fp32
+ * [n_nodes,C], node_labels int64 [n_nodes], src_row int64 [n_nodes] (row of feats each node came from; consumed by
+ * the scatter).  Entries of one domain pass the same three bases.  Node order = [negatives level 0.. | positives level 0..]. */
+int ge_sampler_gather(const void* const* feats, const long long* const* labels, float* const* nodes,
+                      long long* const* node_labels, long long* const* src_row, const long long* n_loc,
+                      const long long* shift, const int* n_neg_all, const int* step, const int* n_pos_pick,
+                      const int* n_neg_pick, const int* neg_all, const int* out_pos, const int* out_neg,
+                      int n_entries, int C, int dtype, ge_stream_t stream);
+/* dfeats[i]: ZERO-FILLED gradient of feats[i]; receives the rows of dnodes[i] at src_row[i] (distinct rows: a scatter). */
+int ge_sampler_scatter(void* const* dfeats, const float* const* dnodes, const long long* const* src_row,
+                       const int* n_pos_pick, const int* n_neg_pick, const int* out_pos, const int* out_neg,
+                       int n_entries, int C, int dtype, ge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

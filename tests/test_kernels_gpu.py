@@ -848,3 +848,53 @@ def test_sampler_labels_kernel_bit_exact(dev, hw, nc, B):
         for l, (a, b) in enumerate(zip(labels, ref)):
             assert torch.equal(a.cpu(), b.reshape(-1).long()), l
             assert counts[l].tolist() == [int((b > 0).sum()), int((b == 0).sum())]
+
+# ---------------------------------------------------------------------------------------- f1: picks + row gather
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shared", [True, False])
+def test_sampler_gather_kernel_equals_the_reference_picks(dev, dtype, shared):
+    """ge_sampler_gather / ge_sampler_scatter against PrototypeComputation.gather (the torch restatement of
+    graph_matching.py:978-1013 that tests/golden/sampler.pt pins): node rows, labels and order bit-exact, and the
+    feature-map gradients equal, over levels that exercise every branch -- more positives than negatives (all
+    negatives kept), strided positives with floor(linspace) negatives, fewer than 100 positives, no positives."""
+    from graphecho_b200.models.graph_matching import PrototypeComputation
+    torch.manual_seed(3)
+    gen = PrototypeComputation(3)
+    hw = [(28, 28), (14, 14), (7, 7), (4, 4), (2, 2)]
+    Bs, Bt, C = 6, 5, 64
+    Ball = Bs + Bt
+    p_pos = [0.7, 0.2, 0.3, 0.02, 0.0]
+
+    def labels_for(B):
+        out = []
+        for (h, w), p in zip(hw, p_pos):
+            lab = torch.where(torch.rand(B * h * w, device=dev) < p, torch.randint(1, 3, (B * h * w,), device=dev),
+                              torch.zeros(B * h * w, dtype=torch.long, device=dev))
+            out.append(lab)
+        return out
+
+    def counts_of(labels):
+        return [[int((l > 0).sum()), int((l == 0).sum())] for l in labels]
+
+    lab_s, lab_t = labels_for(Bs), labels_for(Bt)
+    cl = torch.channels_last
+    if shared:
+        feats = [torch.randn(Ball, C, h, w, device=dev).to(dtype).contiguous(memory_format=cl).requires_grad_() for h, w in hw]
+        doms = [(feats, lab_s, counts_of(lab_s), 0), (feats, lab_t, counts_of(lab_t), Bs)]
+        leaves = feats
+    else:
+        fs = [torch.randn(Bs, C, h, w, device=dev).to(dtype).contiguous(memory_format=cl).requires_grad_() for h, w in hw]
+        ft = [torch.randn(Bt, C, h, w, device=dev).to(dtype).contiguous(memory_format=cl).requires_grad_() for h, w in hw]
+        doms = [(fs, lab_s, counts_of(lab_s), 0), (ft, lab_t, counts_of(lab_t), 0)]
+        leaves = fs + ft
+    ref = [gen.gather(*d) for d in doms]
+    got = gen.gather_pair(*doms)
+    ws = []
+    for (rn, rl, rw), (gn, gl, gw) in zip(ref, got):
+        assert gn.dtype == torch.float32 and gl.dtype == torch.int64
+        assert torch.equal(gn, rn.float()) and torch.equal(gl, rl) and torch.equal(gw, rw)
+        ws.append(torch.randn_like(gn))
+    g_ref = torch.autograd.grad(sum((rn.float() * w).sum() for (rn, _, _), w in zip(ref, ws)), leaves)
+    g_got = torch.autograd.grad(sum((gn * w).sum() for (gn, _, _), w in zip(got, ws)), leaves)
+    for a, b in zip(g_got, g_ref):
+        assert a.dtype == b.dtype and torch.equal(a, b)
