@@ -32,6 +32,8 @@ _SIGNATURES = {
     "ge_sinkhorn_rpm_cluster_size": (c_int, [I, I, I]),
     "ge_sinkhorn_rpm_fwd": (c_int, [P, P, P, P, P, I, I, I, I, I, I, P]),
     "ge_sinkhorn_rpm_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, P]),
+    "ge_matching_loss_fwd": (c_int, [P, P, P, P, P, P, I, I, F, F, P]),
+    "ge_matching_loss_bwd": (c_int, [P, P, P, P, P, P, P, I, I, F, F, P]),
     "ge_sinkhorn_distance_fwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, c_double, P]),
     "ge_sinkhorn_distance_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "ge_knn_graph_set_path": (c_int, [I]),

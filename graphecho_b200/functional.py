@@ -121,6 +121,40 @@ def sinkhorn_rpm_exp(M, n_iters=20, instnorm=True, cluster_size=0):
     return _SinkhornRpm.apply(M, n_iters, instnorm, cluster_size)
 
 
+class _MatchingLossO2O(Function):
+    @staticmethod
+    def forward(ctx, P, lab1, lab2, alpha, gamma):
+        _need_cuda(P, lab1, lab2)
+        Pc, l1, l2 = _f32c(P), _f32c(lab1), _f32c(lab2)
+        N1, N2 = Pc.shape
+        dev = P.device
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        idx = torch.empty(N1, device=dev, dtype=torch.int32)
+        stats = torch.empty(4, device=dev, dtype=torch.float32)
+        call("ge_matching_loss_fwd", ptr(Pc), ptr(l1), ptr(l2), ptr(loss), ptr(idx), ptr(stats), N1, N2,
+             c_float(alpha), c_float(gamma), stream(), work=(4 * N1 * N2, 12 * N1 * N2))
+        ctx.save_for_backward(Pc, l1, l2, idx, stats)
+        ctx.cfg = (float(alpha), float(gamma))
+        return loss[0]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        Pc, l1, l2, idx, stats = ctx.saved_tensors
+        alpha, gamma = ctx.cfg
+        N1, N2 = Pc.shape
+        dP = torch.empty_like(Pc)
+        gc = _f32c(g).reshape(1)
+        call("ge_matching_loss_bwd", ptr(Pc), ptr(l1), ptr(l2), ptr(idx), ptr(stats), ptr(gc), ptr(dP), N1, N2,
+             c_float(alpha), c_float(gamma), stream(), work=(8 * N1 * N2, 14 * N1 * N2))
+        return dP, None, None, None, None
+
+
+def matching_loss_o2o(P, labels_1, labels_2, alpha=0.25, gamma=2.0):
+    """TP + FP focal losses of GModule._forward_aff ('o2o', graph_matching.py:572-590) on the Sinkhorn-normalised P."""
+    return _MatchingLossO2O.apply(P, labels_1, labels_2, alpha, gamma)
+
+
 # ------------------------------------------------------------------------------------------ K5
 class _SinkhornDistance(Function):
     @staticmethod

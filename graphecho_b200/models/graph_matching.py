@@ -191,7 +191,10 @@ class GModule(nn.Module):
         nodes_1, nodes_2 = nodes_1.float(), nodes_2.float()
         if self.with_node_dis and self.node_dis_place == "feat":
             losses["dis_loss"] = self._node_dis_loss(nodes_1, nodes_2)
-        nodes_1, nodes_2 = self.head_in_ln(nodes_1), self.head_in_ln(nodes_2)
+        # head_in_ln is row-wise (Linear / LayerNorm / ReLU): one pass over both domains' rows, then split
+        n_1 = nodes_1.size(0)
+        both = self.head_in_ln(torch.cat([nodes_1, nodes_2], dim=0))
+        nodes_1, nodes_2 = both[:n_1], both[n_1:]
         (nodes_1, nodes_2), (labels_1, labels_2), (weights_1, weights_2) = \
             self._forward_preprocessing_source_target((nodes_1, nodes_2), (labels_1, labels_2), (weights_1, weights_2))
         if self.with_complete_graph:
@@ -240,6 +243,13 @@ class GModule(nn.Module):
                            torch.bincount(tl.long(), minlength=nbin)[:nbin]]).tolist()          # one host sync
         s_cnt, t_cnt = cnt
         present = [c for c in range(nbin) if s_cnt[c] > 0 or t_cnt[c] > 0]
+        if all(s_cnt[c] > 0 and t_cnt[c] > 0 for c in present):
+            # every class lives in both domains (the usual case): class-major regrouping is a stable sort by label
+            self._class_layout = [(int(c), s_cnt[c], t_cnt[c]) for c in present]
+            so, to = torch.sort(sl, stable=True)[1], torch.sort(tl, stable=True)[1]
+            return ((sn.index_select(0, so), tn.index_select(0, to)),
+                    (sl.index_select(0, so).float(), tl.index_select(0, to).float()),
+                    (sw.index_select(0, so), tw.index_select(0, to)))
         S, T, SL, TL, SW, TW = [], [], [], [], [], []
         for c in present:
             ci = int(c)
@@ -302,23 +312,15 @@ class GModule(nn.Module):
         """graph_matching.py:569-599.  'o2o': affinity -> fused instance-norm + Sinkhorn(20) + exp ->
         true-positive (row-wise best same-class entry) and false-positive focal losses."""
         M = self.node_affinity(nodes_1, nodes_2)
-        same = labels_side1.long().unsqueeze(1) == labels_side2.long().unsqueeze(0)     # one_hot @ one_hot^T == 1
         if self.matching_cfg == "o2o":
             M = GF.sinkhorn_rpm_exp(M, 20, True)
-            samef = same.float()
-            idx = (M * samef).max(-1)[1]
-            tp = M.gather(1, idx.unsqueeze(1))
-            tp_loss = self.matching_loss(tp, torch.ones_like(tp)) / len(tp)
-            # false positives = every different-class entry (graph_matching.py:582-588), reduced through the
-            # mask instead of a boolean gather (no host sync): mean focal loss over them / their sum
-            diff = 1.0 - samef
-            a, g = self.matching_loss.alpha, self.matching_loss.gamma
-            # mask BEFORE the log: a same-class entry that saturates to 1.0 would otherwise contribute
-            # -inf * 0 = NaN (forward and backward); the reference gathers the different-class entries only
-            Mfp = torch.where(same, torch.zeros_like(M), M)
-            fp_elem = -(1 - a) * Mfp ** g * torch.log(1 - Mfp)
-            fp_loss = fp_elem.sum() / diff.sum() / Mfp.sum().detach()
-            return tp_loss + fp_loss, M
+            # true positives = the row-wise best same-class entry, false positives = every different-class entry
+            # (graph_matching.py:577-588); one fused kernel each way (GF.matching_loss_o2o).  The different-class
+            # entries are selected by mask, not gathered, and the log is only taken there: a same-class entry that
+            # saturates to 1.0 cannot produce -inf * 0 = NaN.
+            loss = GF.matching_loss_o2o(M, labels_side1, labels_side2, self.matching_loss.alpha, self.matching_loss.gamma)
+            return loss, M
+        same = labels_side1.long().unsqueeze(1) == labels_side2.long().unsqueeze(0)     # one_hot @ one_hot^T == 1
         if self.matching_cfg == "m2m":
             return self.matching_loss(M.sigmoid(), same.float()).mean(), M
         return 0, None

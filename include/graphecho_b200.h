@@ -76,6 +76,18 @@ int ge_sinkhorn_rpm_bwd(const float* M, const float* G, const float* hist_r, con
                         const float* stats, float* dM, int batch, int N1, int N2, int n_iters,
                         int apply_instnorm, int cluster_size, ge_stream_t stream);
 
+/* ---- K4b: 'o2o' matching loss on the Sinkhorn-normalised affinity --------------------------
+ * GModule._forward_aff (models/graph_matching.py:572-590) with BCEFocalLoss (:23-45):
+ *   idx_i = argmax_j P_ij [lab1_i == lab2_j], tp_i = P[i,idx_i], tp_loss = mean_i(-alpha (1-tp_i)^gamma log tp_i) / N1,
+ *   fp_loss = mean over different-class entries of -(1-alpha) P^gamma log(1-P), divided by their (detached) sum of P;
+ *   loss = tp_loss + fp_loss.  One launch forward (one CTA walks the matrix), one element-wise launch backward.
+ * P [N1,N2] fp32; lab1 [N1], lab2 [N2] fp32 class labels; loss [1]; idx int32 [N1] and stats fp32 [4] are saved for the
+ * backward; gout [1] = dLoss/dloss on the device; dP [N1,N2]. */
+int ge_matching_loss_fwd(const float* P, const float* lab1, const float* lab2, float* loss, int* idx, float* stats,
+                         int N1, int N2, float alpha, float gamma, ge_stream_t stream);
+int ge_matching_loss_bwd(const float* P, const float* lab1, const float* lab2, const int* idx, const float* stats,
+                         const float* gout, float* dP, int N1, int N2, float alpha, float gamma, ge_stream_t stream);
+
 /* ---- K5: SinkhornDistance ----------------------------------------------------------------
  * utils/sinkhorn_distance.py:27-86: C_ij = sum_d (x_id-y_jd)^2, <= max_iter log-domain updates
  * with the batch-mean early stop `err < thresh`, pi = exp((-C+u+v)/eps), cost_b = sum pi*C.

@@ -898,3 +898,24 @@ def test_sampler_gather_kernel_equals_the_reference_picks(dev, dtype, shared):
     g_got = torch.autograd.grad(sum((gn * w).sum() for (gn, _, _), w in zip(got, ws)), leaves)
     for a, b in zip(g_got, g_ref):
         assert a.dtype == b.dtype and torch.equal(a, b)
+
+# ---------------------------------------------------------------------------------------- K4b: matching loss
+@pytest.mark.parametrize("n1,n2,nc", [(252, 250, 2), (37, 45, 4), (6, 9, 3), (300, 120, 2)])
+def test_matching_loss_kernel_vs_oracle(dev, n1, n2, nc):
+    """ge_matching_loss_fwd/bwd against the oracle's literal TP/FP focal losses (graph_matching.py:572-590: boolean
+    gathers, BCEFocalLoss means), value and gradient with respect to the Sinkhorn-normalised matrix."""
+    torch.manual_seed(n1 + n2)
+    P = GF.sinkhorn_rpm_exp(torch.randn(n1, n2, device=dev) * 1.5, 20, True).detach()
+    l1 = torch.randint(0, nc, (n1,))
+    l2 = torch.randint(0, nc, (n2,))
+    if n1 == 6:
+        l1[0] = nc - 1
+        l2[l2 == nc - 1] = 0          # a row without any same-class column: the reference's argmax falls on column 0
+    Po = P.cpu().clone().requires_grad_()
+    ref = G.matching_loss_o2o(Po, l1, l2, nc)
+    ref.backward()
+    Pd = P.clone().requires_grad_()
+    got = GF.matching_loss_o2o(Pd, l1.float().to(dev), l2.float().to(dev), 0.25, 2.0)
+    (got * 1.0).backward()
+    close(got, ref, rtol=2e-5, atol=1e-7)
+    close(Pd.grad, Po.grad, rtol=1e-4, atol=1e-9)
