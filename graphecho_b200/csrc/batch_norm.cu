@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(FCH * FLN)
 bn_finalize_stats_kernel(const float* __restrict__ part, SegPlan sp, const float* __restrict__ shift_src,
                          float* __restrict__ save_mean, float* __restrict__ save_rstd,
                          float* __restrict__ running_mean, float* __restrict__ running_var,
-                         long long* __restrict__ num_batches_tracked, int C, float eps, float momentum) {
+                         long long* __restrict__ num_batches_tracked, int C, float eps, float momentum,
+                         int count_scale) {
     __shared__ float sh[FLN][2][FCH];
     const int c = blockIdx.x * FCH + (threadIdx.x % FCH), lane8 = threadIdx.x / FCH;
     const bool owner = lane8 == 0 && c < C;
@@ -151,7 +152,10 @@ bn_finalize_stats_kernel(const float* __restrict__ part, SegPlan sp, const float
             const float mean = md + shift;
             save_mean[s * C + c] = mean;
             save_rstd[s * C + c] = 1.f / sqrtf(var + eps);
-            const float unbiased = Ps > 1 ? var * ((float)Ps / (float)(Ps - 1)) : var;
+            // count_scale > 1: the rows are AVERAGES over that many equal-sized ranks (SyncBatchNorm): the statistics are
+            // those of Ps * count_scale pixels
+            const long long Pt = Ps * count_scale;
+            const float unbiased = Pt > 1 ? var * ((float)Pt / (float)(Pt - 1)) : var;
             rm = (1.f - momentum) * rm + momentum * mean;
             rv = (1.f - momentum) * rv + momentum * unbiased;
         }
@@ -435,6 +439,61 @@ size_t bn_ws_rows(long long P, int C) {
     return a > b ? a : b;
 }
 
+// rows -> per-segment sums in the row layout ([s][2][C]) the forward finalize reads (SyncBatchNorm exchange buffer)
+__global__ void __launch_bounds__(FCH * FLN)
+bn_rows_to_segments_kernel(const float* __restrict__ part, SegPlan sp, float* __restrict__ sums, int C) {
+    __shared__ float sh[FLN][2][FCH];
+    const int c = blockIdx.x * FCH + (threadIdx.x % FCH), lane8 = threadIdx.x / FCH;
+    const bool owner = lane8 == 0 && c < C;
+    const int nseg = sp.nseg();
+    for (int s = 0; s < nseg; ++s) {
+        const int first = s == 0 ? 0 : sp.chunks0, n = s == 0 ? sp.chunks0 : sp.chunks - sp.chunks0;
+        float sa, sb;
+        reduce_parts(part + (size_t)first * 2 * C, n, C, c, lane8, sh, sa, sb);
+        if (owner) {
+            sums[(size_t)s * 2 * C + c] = sa;
+            sums[(size_t)s * 2 * C + C + c] = sb;
+        }
+    }
+}
+
+int bn_bwd_reduce_stage(const void* dy, const unsigned short* mk, const void* x, const float* mean, const float* rstd,
+                        float* part, float* seg_sums, float* dgamma, float* dbeta, int dtype, long long P, long long P_split,
+                        int C, cudaStream_t st) {
+    const SegPlan sp = bn_plan(P, P_split, C);
+    const size_t smem = bn_smem(C);
+    static size_t c0 = 0, c1 = 0;
+    if (dtype == GE_DTYPE_F32) {
+        if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(bn_partial_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_bwd(attr)"); c0 = smem; }
+        bn_partial_bwd_kernel<float><<<sp.chunks, BN_THREADS, smem, st>>>((const float*)dy, mk, (const float*)x,
+                                                                          mean, rstd, part, sp, C);
+    } else {
+        if (smem > c1) { GE_CUDA(cudaFuncSetAttribute(bn_partial_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_bwd(attr)"); c1 = smem; }
+        bn_partial_bwd_kernel<bf16><<<sp.chunks, BN_THREADS, smem, st>>>((const bf16*)dy, mk, (const bf16*)x,
+                                                                         mean, rstd, part, sp, C);
+    }
+    GE_CHECK_LAUNCH("ge_bn_bwd(partial)");
+    bn_finalize_bwd_kernel<<<ge::cdiv(C, FCH), FCH * FLN, 0, st>>>(part, sp, seg_sums, dgamma, dbeta, C);
+    GE_CHECK_LAUNCH("ge_bn_bwd(finalize)");
+    return GE_OK;
+}
+
+int bn_bwd_apply_stage(const void* dy, const unsigned short* mk, const void* x, const float* gamma, const float* mean,
+                       const float* rstd, const float* seg_sums, void* dx, void* dres, int dtype, long long P,
+                       long long P_split, int C, cudaStream_t st) {
+    const long long P0 = (P_split > 0 && P_split < P) ? P_split : P;
+    const long long total4 = ge::cdivll(P, BPIX4) * (C / 4);
+    const unsigned blocks4 = (unsigned)ge::cdivll(total4, 256);
+    if (dtype == GE_DTYPE_F32)
+        bn_apply_bwd4_kernel<float><<<blocks4, 256, 0, st>>>((const float*)dy, mk, (const float*)x, mean, rstd,
+            gamma, seg_sums, (float*)dx, (float*)dres, P, P0, C);
+    else
+        bn_apply_bwd4_kernel<bf16><<<blocks4, 256, 0, st>>>((const bf16*)dy, mk, (const bf16*)x, mean, rstd,
+            gamma, seg_sums, (bf16*)dx, (bf16*)dres, P, P0, C);
+    GE_CHECK_LAUNCH("ge_bn_bwd(apply)");
+    return GE_OK;
+}
+
 }  // namespace
 
 extern "C" int ge_bn_set_path(int path) {
@@ -504,7 +563,7 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
     } else { ge_set_error("ge_bn_fwd_train: unsupported dtype %d", dtype); return GE_ERR_DTYPE; }
     GE_CHECK_LAUNCH("ge_bn_fwd_train(stats)");
     bn_finalize_stats_kernel<<<ge::cdiv(C, FCH), FCH * FLN, 0, st>>>(part, sp, shift, save_mean, save_rstd,
-                                                               running_mean, running_var, num_batches_tracked, C, eps, momentum);
+                                                               running_mean, running_var, num_batches_tracked, C, eps, momentum, 1);
     GE_CHECK_LAUNCH("ge_bn_fwd_train(finalize)");
     const unsigned blocks4 = (unsigned)ge::cdivll(ge::cdivll(P, FPIX4) * (C / 4), 256);
     unsigned short* mk = relu ? static_cast<unsigned short*>(relu_mask) : nullptr;
@@ -522,15 +581,15 @@ extern "C" int ge_bn_fwd_train(const void* x, const void* residual, const float*
 // ge_conv1x1_bn_stats, which produced x): finalize + apply only -- the statistics pass over x is gone.
 // part fp32 [rows][2][C]: sums of (x - shift) and (x - shift)^2 with shift = running_mean as it is BEFORE this call
 // (zero when running_mean is NULL); rows [0, rows_segment0) cover pixels [0, P_split), the rest [P_split, P).
-extern "C" int ge_bn_fwd_train_prestat(const void* x, const void* residual, const float* gamma, const float* beta,
+static int bn_fwd_from_rows(const char* name, int count_scale, const void* x, const void* residual, const float* gamma, const float* beta,
                                        float* running_mean, float* running_var, long long* num_batches_tracked,
                                        float momentum, float eps, void* out, float* save_mean, float* save_rstd,
                                        void* relu_mask, const float* part, int rows, int rows_segment0,
                                        int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream) {
-    GE_REQUIRE(x && gamma && beta && out && save_mean && save_rstd && part, GE_ERR_ARG, "ge_bn_fwd_train_prestat: null pointer");
-    GE_REQUIRE(P > 0 && C > 0 && P_split >= 0 && P_split <= P && rows > 0, GE_ERR_ARG, "ge_bn_fwd_train_prestat: bad dimension");
-    GE_REQUIRE(C % 8 == 0, GE_ERR_SHAPE, "ge_bn_fwd_train_prestat: C=%d must be a multiple of 8", C);
-    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_fwd_train_prestat: unsupported dtype %d", dtype);
+    GE_REQUIRE(x && gamma && beta && out && save_mean && save_rstd && part, GE_ERR_ARG, "%s: null pointer", name);
+    GE_REQUIRE(P > 0 && C > 0 && P_split >= 0 && P_split <= P && rows > 0, GE_ERR_ARG, "%s: bad dimension", name);
+    GE_REQUIRE(C % 8 == 0, GE_ERR_SHAPE, "ge_bn_fwd_train_prestat/sync: C=%d must be a multiple of 8", C);
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_fwd_train_prestat/sync: unsupported dtype %d", dtype);
     cudaStream_t st = (cudaStream_t)stream;
     SegPlan sp;
     sp.P = P;
@@ -538,11 +597,11 @@ extern "C" int ge_bn_fwd_train_prestat(const void* x, const void* residual, cons
     sp.chunks = rows;
     sp.chunks0 = sp.P0 < P ? rows_segment0 : rows;
     sp.ppc0 = sp.ppc1 = 0;
-    GE_REQUIRE(sp.chunks0 >= 1 && (sp.P0 == P || sp.chunks0 < rows), GE_ERR_ARG, "ge_bn_fwd_train_prestat: bad segment rows");
+    GE_REQUIRE(sp.chunks0 >= 1 && (sp.P0 == P || sp.chunks0 < rows), GE_ERR_ARG, "%s: bad segment rows", name);
     const float* shift = running_mean != nullptr ? running_mean : save_mean;
     if (running_mean == nullptr) GE_CUDA(cudaMemsetAsync(save_mean, 0, (size_t)C * sizeof(float), st), "ge_bn_fwd_train_prestat(memset)");
     bn_finalize_stats_kernel<<<ge::cdiv(C, FCH), FCH * FLN, 0, st>>>(part, sp, shift, save_mean, save_rstd,
-                                                               running_mean, running_var, num_batches_tracked, C, eps, momentum);
+                                                               running_mean, running_var, num_batches_tracked, C, eps, momentum, count_scale);
     GE_CHECK_LAUNCH("ge_bn_fwd_train_prestat(finalize)");
     const unsigned blocks4 = (unsigned)ge::cdivll(ge::cdivll(P, FPIX4) * (C / 4), 256);
     unsigned short* mk = relu ? static_cast<unsigned short*>(relu_mask) : nullptr;
@@ -554,6 +613,16 @@ extern "C" int ge_bn_fwd_train_prestat(const void* x, const void* residual, cons
                                                                 gamma, beta, (bf16*)out, mk, P, sp.P0, C, eps, relu);
     GE_CHECK_LAUNCH("ge_bn_fwd_train_prestat(apply)");
     return GE_OK;
+}
+
+extern "C" int ge_bn_fwd_train_prestat(const void* x, const void* residual, const float* gamma, const float* beta,
+                                       float* running_mean, float* running_var, long long* num_batches_tracked,
+                                       float momentum, float eps, void* out, float* save_mean, float* save_rstd,
+                                       void* relu_mask, const float* part, int rows, int rows_segment0,
+                                       int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream) {
+    return bn_fwd_from_rows("ge_bn_fwd_train_prestat", 1, x, residual, gamma, beta, running_mean, running_var,
+                            num_batches_tracked, momentum, eps, out, save_mean, save_rstd, relu_mask, part, rows,
+                            rows_segment0, dtype, P, P_split, C, relu, stream);
 }
 
 extern "C" int ge_bn_fwd_eval(const void* x, const void* residual, const float* gamma, const float* beta,
@@ -608,31 +677,88 @@ extern "C" int ge_bn_bwd(const void* dy, const void* relu_mask, const void* x, c
                             : coop_launch(ge_bn_coop::bn_bwd_coop_kernel<bf16, false>, cp.G, smemc, args, st, &a[3], "ge_bn_bwd(coop)");
         }
     }
+    if (int rc = bn_bwd_reduce_stage(dy, mk, x, mean, rstd, part, seg_sums, dgamma, dbeta, dtype, P, P_split, C, st)) return rc;
+    return bn_bwd_apply_stage(dy, mk, x, gamma, mean, rstd, seg_sums, dx, dres, dtype, P, P_split, C, st);
+}
+
+// ---- SyncBatchNorm: the same kernels with the cross-rank exchange between the statistics and the apply stages ------
+// The caller (functional._SyncBnAct) all-reduces the small per-segment sums with op=AVG between the two calls of each
+// direction; every rank holds the same number of pixels per segment (the path shards evenly), so an average of the
+// sums over ranks divided by the local pixel count is the global statistic.
+
+// Stage 1 forward: sums fp32 [nseg][2][C] = per-segment sums of (x - shift) and (x - shift)^2 over THIS rank's pixels;
+// shift = running_mean (identical on every rank) or NULL for a zero shift.  workspace: ge_bn_workspace_bytes(P, C).
+extern "C" int ge_bn_sync_stats(const void* x, const float* shift, float* sums, void* workspace, size_t workspace_bytes,
+                                int dtype, long long P, long long P_split, int C, ge_stream_t stream) {
+    GE_REQUIRE(x && sums && workspace, GE_ERR_ARG, "ge_bn_sync_stats: null pointer");
+    GE_REQUIRE(P > 0 && C > 0 && P_split >= 0 && P_split <= P, GE_ERR_ARG, "ge_bn_sync_stats: bad dimension");
+    GE_REQUIRE(bn_shape_ok(C), GE_ERR_SHAPE, "ge_bn_sync_stats: unsupported channel count C=%d (C%%8==0, C/8 | 256)", C);
+    GE_REQUIRE(workspace_bytes >= ge_bn_workspace_bytes(P, C), GE_ERR_ARG, "ge_bn_sync_stats: workspace too small");
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_sync_stats: unsupported dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
     const SegPlan sp = bn_plan(P, P_split, C);
     const size_t smem = bn_smem(C);
+    float* part = static_cast<float*>(workspace);
+    float* zero = part + bn_ws_rows(P, C) * 2 * C;           // the [4][C] tail of the workspace
+    if (shift == nullptr) {
+        GE_CUDA(cudaMemsetAsync(zero, 0, (size_t)C * sizeof(float), st), "ge_bn_sync_stats(memset)");
+        shift = zero;
+    }
     static size_t c0 = 0, c1 = 0;
     if (dtype == GE_DTYPE_F32) {
-        if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(bn_partial_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_bwd(attr)"); c0 = smem; }
+        if (smem > c0) { GE_CUDA(cudaFuncSetAttribute(bn_partial_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_sync_stats(attr)"); c0 = smem; }
+        bn_partial_stats_kernel<float><<<sp.chunks, BN_THREADS, smem, st>>>((const float*)x, shift, part, sp, C);
     } else {
-        if (smem > c1) { GE_CUDA(cudaFuncSetAttribute(bn_partial_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_bwd(attr)"); c1 = smem; }
+        if (smem > c1) { GE_CUDA(cudaFuncSetAttribute(bn_partial_stats_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ge_bn_sync_stats(attr)"); c1 = smem; }
+        bn_partial_stats_kernel<bf16><<<sp.chunks, BN_THREADS, smem, st>>>((const bf16*)x, shift, part, sp, C);
     }
-    if (dtype == GE_DTYPE_F32)
-        bn_partial_bwd_kernel<float><<<sp.chunks, BN_THREADS, smem, st>>>((const float*)dy, mk, (const float*)x,
-                                                                          mean, rstd, part, sp, C);
-    else
-        bn_partial_bwd_kernel<bf16><<<sp.chunks, BN_THREADS, smem, st>>>((const bf16*)dy, mk, (const bf16*)x,
-                                                                         mean, rstd, part, sp, C);
-    GE_CHECK_LAUNCH("ge_bn_bwd(partial)");
-    bn_finalize_bwd_kernel<<<ge::cdiv(C, FCH), FCH * FLN, 0, st>>>(part, sp, seg_sums, dgamma, dbeta, C);
-    GE_CHECK_LAUNCH("ge_bn_bwd(finalize)");
-    const long long total4 = ge::cdivll(P, BPIX4) * (C / 4);
-    const unsigned blocks4 = (unsigned)ge::cdivll(total4, 256);
-    if (dtype == GE_DTYPE_F32)
-        bn_apply_bwd4_kernel<float><<<blocks4, 256, 0, st>>>((const float*)dy, mk, (const float*)x, mean, rstd,
-            gamma, seg_sums, (float*)dx, (float*)dres, P, sp.P0, C);
-    else
-        bn_apply_bwd4_kernel<bf16><<<blocks4, 256, 0, st>>>((const bf16*)dy, mk, (const bf16*)x, mean, rstd,
-            gamma, seg_sums, (bf16*)dx, (bf16*)dres, P, sp.P0, C);
-    GE_CHECK_LAUNCH("ge_bn_bwd(apply)");
+    GE_CHECK_LAUNCH("ge_bn_sync_stats(partial)");
+    bn_rows_to_segments_kernel<<<ge::cdiv(C, FCH), FCH * FLN, 0, st>>>(part, sp, sums, C);
+    GE_CHECK_LAUNCH("ge_bn_sync_stats(segments)");
     return GE_OK;
+}
+
+// Stage 2 forward: sums_avg = the all-reduced (AVG over `world` ranks) output of ge_bn_sync_stats.  Everything else as
+// ge_bn_fwd_train: save_mean / save_rstd [nseg][C], running statistics updated once per segment with the unbiased
+// variance of P_segment * world pixels, num_batches_tracked += nseg, out, ReLU mask.
+extern "C" int ge_bn_sync_fwd_apply(const void* x, const void* residual, const float* gamma, const float* beta,
+                                    float* running_mean, float* running_var, long long* num_batches_tracked,
+                                    float momentum, float eps, void* out, float* save_mean, float* save_rstd,
+                                    void* relu_mask, const float* sums_avg, int world,
+                                    int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream) {
+    GE_REQUIRE(world >= 1, GE_ERR_ARG, "ge_bn_sync_fwd_apply: world=%d", world);
+    const int nseg = (P_split > 0 && P_split < P) ? 2 : 1;
+    return bn_fwd_from_rows("ge_bn_sync_fwd_apply", world, x, residual, gamma, beta, running_mean, running_var,
+                            num_batches_tracked, momentum, eps, out, save_mean, save_rstd, relu_mask, sums_avg, nseg, 1,
+                            dtype, P, P_split, C, relu, stream);
+}
+
+// Stage 1 backward: seg_sums fp32 [2][nseg][C] = per-segment sums of dy*relu' and dy*relu'*xhat over this rank's pixels;
+// dgamma / dbeta = this rank's parameter gradients (the gradient exchange averages them like every other parameter).
+extern "C" int ge_bn_sync_bwd_reduce(const void* dy, const void* relu_mask, const void* x, const float* mean,
+                                     const float* rstd, float* seg_sums, float* dgamma, float* dbeta,
+                                     void* workspace, size_t workspace_bytes,
+                                     int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream) {
+    GE_REQUIRE(dy && x && mean && rstd && seg_sums && dgamma && dbeta && workspace, GE_ERR_ARG, "ge_bn_sync_bwd_reduce: null pointer");
+    GE_REQUIRE(!relu || relu_mask, GE_ERR_ARG, "ge_bn_sync_bwd_reduce: the forward's ReLU mask is needed");
+    GE_REQUIRE(P > 0 && C > 0 && P_split >= 0 && P_split <= P, GE_ERR_ARG, "ge_bn_sync_bwd_reduce: bad dimension");
+    GE_REQUIRE(bn_shape_ok(C), GE_ERR_SHAPE, "ge_bn_sync_bwd_reduce: unsupported channel count C=%d", C);
+    GE_REQUIRE(workspace_bytes >= ge_bn_workspace_bytes(P, C), GE_ERR_ARG, "ge_bn_sync_bwd_reduce: workspace too small");
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_sync_bwd_reduce: unsupported dtype %d", dtype);
+    const unsigned short* mk = relu ? static_cast<const unsigned short*>(relu_mask) : nullptr;
+    return bn_bwd_reduce_stage(dy, mk, x, mean, rstd, static_cast<float*>(workspace), seg_sums, dgamma, dbeta, dtype, P, P_split,
+                               C, (cudaStream_t)stream);
+}
+
+// Stage 2 backward: seg_sums_avg = the all-reduced (AVG) output of ge_bn_sync_bwd_reduce.
+extern "C" int ge_bn_sync_bwd_apply(const void* dy, const void* relu_mask, const void* x, const float* gamma,
+                                    const float* mean, const float* rstd, const float* seg_sums_avg, void* dx, void* dres,
+                                    int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream) {
+    GE_REQUIRE(dy && x && gamma && mean && rstd && seg_sums_avg && dx, GE_ERR_ARG, "ge_bn_sync_bwd_apply: null pointer");
+    GE_REQUIRE(!relu || relu_mask, GE_ERR_ARG, "ge_bn_sync_bwd_apply: the forward's ReLU mask is needed");
+    GE_REQUIRE(P > 0 && C > 0 && P_split >= 0 && P_split <= P, GE_ERR_ARG, "ge_bn_sync_bwd_apply: bad dimension");
+    GE_REQUIRE(C % 4 == 0, GE_ERR_SHAPE, "ge_bn_sync_bwd_apply: unsupported channel count C=%d", C);
+    GE_REQUIRE(dtype == GE_DTYPE_F32 || dtype == GE_DTYPE_BF16, GE_ERR_DTYPE, "ge_bn_sync_bwd_apply: unsupported dtype %d", dtype);
+    const unsigned short* mk = relu ? static_cast<const unsigned short*>(relu_mask) : nullptr;
+    return bn_bwd_apply_stage(dy, mk, x, gamma, mean, rstd, seg_sums_avg, dx, dres, dtype, P, P_split, C, (cudaStream_t)stream);
 }

@@ -198,8 +198,7 @@ class GModule(nn.Module):
         (nodes_1, nodes_2), (labels_1, labels_2), (weights_1, weights_2) = \
             self._forward_preprocessing_source_target((nodes_1, nodes_2), (labels_1, labels_2), (weights_1, weights_2))
         if self.with_complete_graph:
-            nodes_1, edges_1 = self._forward_intra_domain_graph(nodes_1)
-            nodes_2, edges_2 = self._forward_intra_domain_graph(nodes_2)
+            (nodes_1, edges_1), (nodes_2, edges_2) = self.intra_domain_graph.forward_pair(nodes_1, nodes_1, nodes_2, nodes_2)
         if getattr(self, "defer_seed_update", False):
             self._pending_seed = (nodes_1.detach(), labels_1, nodes_2.detach(), labels_2, getattr(self, "_class_layout", None))
             self._class_layout = None
@@ -295,8 +294,8 @@ class GModule(nn.Module):
             g = torch.cat([nodes_1, nodes_2], dim=0)
             g = self.cross_domain_graph(g, g, g)[0]
             return g[:n_1], g[n_1:]
-        nodes2_enhanced = self.cross_domain_graph(nodes_1, nodes_1, nodes_2)[0]
-        nodes1_enhanced = self.cross_domain_graph(nodes_2, nodes_2, nodes_1)[0]
+        # nodes2_enhanced = cross(nodes_1, nodes_1, nodes_2)[0], nodes1_enhanced = cross(nodes_2, nodes_2, nodes_1)[0]
+        (nodes2_enhanced, _), (nodes1_enhanced, _) = self.cross_domain_graph.forward_pair(nodes_1, nodes_2, nodes_2, nodes_1)
         return nodes1_enhanced, nodes2_enhanced
 
     def _forward_node_loss(self, nodes, labels, weights=None):

@@ -70,6 +70,43 @@ class MultiHeadAttention(nn.Module):
         return output.squeeze(), attention.squeeze()
 
 
+def _mha_forward_pair(self, kv_a, q_a, kv_b, q_b):
+    """Two version-'v2', single-head calls of ONE module, forward(kv_a, kv_a, q_a) and forward(kv_b, kv_b, q_b), with the
+    row-wise parts (the three projections, the output projection, dropout, residual and LayerNorm) run once over the
+    concatenated rows and only the two attention products kept apart.  Same arithmetic per row as two separate calls
+    (transformer.py:45-75); roughly a third fewer launches forward and backward on the host-driven graph-module stream.
+    Returns ((out_a, attn_a), (out_b, attn_b))."""
+    assert self.version == "v2" and self.num_heads == 1
+    with torch.autocast("cuda", enabled=False):
+        kv_a, q_a, kv_b, q_b = kv_a.float(), q_a.float(), kv_b.float(), q_b.float()
+        na = kv_a.size(0)
+        same_q = q_a is kv_a and q_b is kv_b          # self-attention of two node sets
+        swapped = q_a is kv_b and q_b is kv_a         # each set attends over the other one
+        kv = torch.cat([kv_a, kv_b], dim=0)
+        q_in = kv if (same_q or swapped) else torch.cat([q_a, q_b], dim=0)
+        K, V, Q = self.linear_k(kv), self.linear_v(kv), self.linear_q(q_in)
+        scale = (self.dim_per_head // self.num_heads) ** -0.5
+        att = self.dot_product_attention
+
+        def core(Qx, Kx, Vx):
+            attention = att.dropout(att.softmax((torch.mm(Qx, Kx.t()) * scale).unsqueeze(0))).squeeze(0)
+            return torch.mm(attention, Vx), attention
+
+        if swapped:      # rows of q_in are [q_b ; q_a]
+            ctx_a, attn_a = core(Q[na:], K[:na], V[:na])
+            ctx_b, attn_b = core(Q[:na], K[na:], V[na:])
+            out = self.layer_norm(q_in + self.dropout(self.linear_final(torch.cat([ctx_b, ctx_a], dim=0))))
+            return (out[na:], attn_a), (out[:na], attn_b)
+        ma = q_a.size(0)
+        ctx_a, attn_a = core(Q[:ma], K[:na], V[:na])
+        ctx_b, attn_b = core(Q[ma:], K[na:], V[na:])
+        out = self.layer_norm(q_in + self.dropout(self.linear_final(torch.cat([ctx_a, ctx_b], dim=0))))
+        return (out[:ma], attn_a), (out[ma:], attn_b)
+
+
+MultiHeadAttention.forward_pair = _mha_forward_pair
+
+
 class CrossGraph(nn.Module):
     """transformer.py:115-160 (never instantiated by the trainers; API surface)."""
 

@@ -67,3 +67,19 @@ def test_fp16_hi_lo_split_inner_product_is_fp32_accurate():
     err_fp32 = ((x * y).sum(1).double() - truth).abs()
     assert err_split.max() < 1e-7                       # distances are 2 - 2*ip: well inside the 2e-6 near-tie window
     assert err_split.mean() < 3 * err_fp32.mean() + 1e-9
+
+
+def test_attention_forward_pair_equals_two_calls():
+    """MultiHeadAttention.forward_pair (projections / output block shared over two node sets, attention products apart)
+    reproduces two separate version-'v2' calls (transformer.py:45-75) for the self-, cross- and general patterns."""
+    import torch
+    from graphecho_b200.models.transformer import MultiHeadAttention
+    torch.manual_seed(0)
+    m = MultiHeadAttention(256, 1, dropout=0.1, version="v2").eval()
+    a, b, c, d = torch.randn(37, 256), torch.randn(45, 256), torch.randn(11, 256), torch.randn(13, 256)
+    for kv_a, q_a, kv_b, q_b in ((a, a, b, b), (a, b, b, a), (a, c, b, d)):
+        (o1, e1), (o2, e2) = m.forward_pair(kv_a, q_a, kv_b, q_b)
+        r1, f1 = m(kv_a, kv_a, q_a)
+        r2, f2 = m(kv_b, kv_b, q_b)
+        for x, y in ((o1, r1), (e1, f1), (o2, r2), (e2, f2)):
+            assert x.shape == y.shape and torch.allclose(x, y, rtol=1e-5, atol=1e-6)
