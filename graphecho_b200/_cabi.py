@@ -67,6 +67,10 @@ _SIGNATURES = {
     "ge_conv1x1_bn_stats": (c_int, [P, P, P, P, P, L, L, I, I, P]),
     "ge_bn_fwd_eval": (c_int, [P, P, P, P, P, P, F, P, I, L, I, I, P]),
     "ge_bn_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, Z, I, L, L, I, I, P]),
+    "ge_bn_sync_stats": (c_int, [P, P, P, P, Z, I, L, L, I, P]),
+    "ge_bn_sync_fwd_apply": (c_int, [P, P, P, P, P, P, P, F, F, P, P, P, P, P, I, I, L, L, I, I, P]),
+    "ge_bn_sync_bwd_reduce": (c_int, [P, P, P, P, P, P, P, P, P, Z, I, L, L, I, I, P]),
+    "ge_bn_sync_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, P, I, L, L, I, I, P]),
     "ge_tgcn_recurrence_supported": (c_int, [I, I, I, I, I, I]),
     "ge_tgcn_recurrence_fwd": (c_int, [P, P, P, P, P, P, P, I, I, I, I, I, P]),
     "ge_tgcn_recurrence_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P]),

@@ -301,7 +301,12 @@ class UDAEngine:
         self.network = FPN([2, 4, 23, 3], num_classes=nc, in_channel=1, back_bone=cfg.backbone).to(device)
         self.network = self.network.to(memory_format=torch.channels_last)
         if world_size > 1 and cfg.sync_bn:
-            self.network = nn.SyncBatchNorm.convert_sync_batchnorm(self.network)
+            # the per-layer statistics exchanges run inside the trunk's CUDA graphs on the compute stream while the
+            # gradient buckets travel on the communication stream: they need their own communicator (one NCCL
+            # communicator must not be used from two streams at once)
+            import torch.distributed as dist
+            self.bn_group = dist.new_group(backend="nccl") if dist.get_backend() == "nccl" else None
+            self.network = nn.SyncBatchNorm.convert_sync_batchnorm(self.network, process_group=self.bn_group)
         self._lower_raw, self._upper_raw, self._head_raw = _TrunkLower(self.network), _TrunkUpper(self.network), _Head(self.network)
         self._lower, self._upper, self._head = self._lower_raw, self._upper_raw, self._head_raw
         self.aux: dict[str, nn.Module] = {}
@@ -363,8 +368,6 @@ class UDAEngine:
         change).  Buffers (BatchNorm running statistics, seed banks) are snapshotted before the warm-up / capture
         executions on dummy inputs and restored afterwards: capturing leaves no trace in the model state."""
         cfg, dev = self.cfg, self.device
-        if self.world > 1 and cfg.sync_bn:
-            raise RuntimeError("cuda_graphs with SyncBatchNorm is not supported: use sync_bn=False")
         ns = n_frames // 2 if n_source is None else int(n_source)
         bufs = self._buffers()
         snapshot = [b.detach().clone() for b in bufs]

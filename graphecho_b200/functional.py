@@ -683,11 +683,97 @@ class _BnAct(Function):
         return dx, dres, dgb[0].to(gdt), dgb[1].to(bdt), None, None, None, None, None, None, None
 
 
+class _SyncBnAct(Function):
+    """Training-mode SyncBatchNorm (+ residual) (+ ReLU) on an NHWC map: the fused BatchNorm kernels with the two small
+    cross-rank exchanges (per-segment sums, averaged over the process group) between their statistics and apply stages.
+    What nn.SyncBatchNorm does under DDP (the reference's intent, train_cardiac_uda.py:142), per domain segment; the
+    all-reduces are NCCL collectives on the current stream, so the whole layer can be captured in a CUDA graph."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, nbt, momentum, eps, relu, split, group, world):
+        import torch.distributed as dist
+        _need_cuda(x, residual, gamma, beta)
+        xc = _nhwc_view(x)
+        N, C, H, W = xc.shape
+        P = N * H * W
+        P_split = split * H * W if 0 < split < N else 0
+        nseg = 2 if P_split else 1
+        rc = _nhwc_view(residual.to(xc.dtype)) if residual is not None else None
+        g, b = _f32c(gamma), _f32c(beta)
+        dev = x.device
+        nbytes = _cabi.lib().ge_bn_workspace_bytes(P, C)
+        if nbytes == 0:
+            raise _cabi.GraphEchoNativeError(f"fused BatchNorm does not support C={C}")
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        sums = torch.empty((nseg, 2, C), device=dev, dtype=torch.float32)
+        dt = _dtype_code(xc)
+        es = xc.element_size()
+        call("ge_bn_sync_stats", ptr(xc), ptr(running_mean), ptr(sums), ptr(ws), c_size_t(nbytes), dt, c_longlong(P),
+             c_longlong(P_split), C, stream(), work=(P * C * es, 3 * P * C))
+        if world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.AVG, group=group)
+        out = torch.empty_like(xc)
+        save = torch.empty((2, nseg, C), device=dev, dtype=torch.float32)
+        mask = torch.empty(_cabi.lib().ge_bn_relu_mask_bytes(P, C), device=dev, dtype=torch.uint8) if relu else None
+        call("ge_bn_sync_fwd_apply", ptr(xc), ptr(rc), ptr(g), ptr(b), ptr(running_mean), ptr(running_var), ptr(nbt),
+             c_float(momentum), c_float(eps), ptr(out), ptr(save[0]), ptr(save[1]), ptr(mask), ptr(sums), int(world),
+             dt, c_longlong(P), c_longlong(P_split), C, int(relu), stream(),
+             work=(P * C * es * (2 + (1 if rc is not None else 0)), 5 * P * C))
+        ctx.save_for_backward(xc, mask, g, save)
+        ctx.cfg = (P, P_split, C, bool(relu), rc is not None, gamma.dtype, beta.dtype, group, int(world))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        import torch.distributed as dist
+        xc, mask, g, save = ctx.saved_tensors
+        P, P_split, C, relu, has_res, gdt, bdt, group, world = ctx.cfg
+        nseg = 2 if P_split else 1
+        d = _nhwc_view(dout.to(xc.dtype))
+        dev = d.device
+        dgb = torch.empty((2, C), device=dev, dtype=torch.float32)
+        seg = torch.empty((2, nseg, C), device=dev, dtype=torch.float32)
+        nbytes = _cabi.lib().ge_bn_workspace_bytes(P, C)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        dt = _dtype_code(xc)
+        es = xc.element_size()
+        call("ge_bn_sync_bwd_reduce", ptr(d), ptr(mask), ptr(xc), ptr(save[0]), ptr(save[1]), ptr(seg), ptr(dgb[0]), ptr(dgb[1]),
+             ptr(ws), c_size_t(nbytes), dt, c_longlong(P), c_longlong(P_split), C, int(relu), stream(),
+             work=(P * C * es * 2 + (P * C // 8 if relu else 0), 8 * P * C))
+        if world > 1:
+            dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=group)
+        dx = torch.empty_like(xc)
+        dres = torch.empty_like(xc) if has_res else None
+        call("ge_bn_sync_bwd_apply", ptr(d), ptr(mask), ptr(xc), ptr(g), ptr(save[0]), ptr(save[1]), ptr(seg), ptr(dx), ptr(dres),
+             dt, c_longlong(P), c_longlong(P_split), C, int(relu), stream(),
+             work=(P * C * es * (3 + (1 if has_res else 0)) + (P * C // 8 if relu else 0), 8 * P * C))
+        return dx, dres, dgb[0].to(gdt), dgb[1].to(bdt), None, None, None, None, None, None, None, None, None
+
+
+def _sync_bn_group(bn):
+    """(process group, world size) of an nn.SyncBatchNorm in training mode, or None when it has to fall back."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    group = bn.process_group if bn.process_group is not None else dist.group.WORLD
+    if dist.get_backend(group) != "nccl":
+        return None
+    return group, dist.get_world_size(group)
+
+
 def bn_act(x, bn, residual=None, relu=True):
     """relu(BatchNorm2d(x) + residual) with `bn` an nn.BatchNorm2d (parameters / buffers are read and,
     in training mode, updated exactly as the module would; under `domain_split` exactly as two calls on the two
     halves would).  Other norm types (e.g. SyncBatchNorm) fall back to the module itself."""
     split = _BN_SPLIT if 0 < _BN_SPLIT < x.shape[0] else 0
+    if (type(bn) is torch.nn.SyncBatchNorm and bn.training and bn.affine and bn.track_running_stats
+            and bn.momentum is not None and x.is_cuda and x.dim() == 4 and bn.num_features % 8 == 0
+            and _cabi.lib().ge_bn_workspace_bytes(x.shape[0] * x.shape[2] * x.shape[3], bn.num_features) > 0):
+        gw = _sync_bn_group(bn)
+        if gw is not None:
+            return _SyncBnAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                                    float(bn.momentum), float(bn.eps), bool(relu), int(split), gw[0], gw[1])
     if type(bn) is not torch.nn.BatchNorm2d or not bn.affine or (bn.training and bn.momentum is None):
         if split and bn.training:
             y = torch.cat([bn(x[:split]), bn(x[split:])], dim=0)

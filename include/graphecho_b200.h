@@ -246,6 +246,30 @@ int ge_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float*
               float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
               int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream);
 
+/* SyncBatchNorm (the reference's intent under DDP, train_cardiac_uda.py:142): the same kernels, split around the two
+ * cross-rank exchanges.  The caller all-reduces `sums` / `seg_sums` with op = AVG over `world` equally loaded ranks
+ * between stage 1 and stage 2 of each direction (NCCL on the same stream: graph-capturable).
+ *   ge_bn_sync_stats      : sums fp32 [nseg][2][C] = per-segment sums of (x - shift), (x - shift)^2 over this rank's
+ *                           pixels; shift = running_mean (identical on all ranks) or NULL.
+ *   ge_bn_sync_fwd_apply  : as ge_bn_fwd_train from the averaged sums (running variance unbiased over P_seg * world).
+ *   ge_bn_sync_bwd_reduce : seg_sums fp32 [2][nseg][C] = per-segment sums of dy*relu', dy*relu'*xhat; dgamma, dbeta of
+ *                           this rank (the gradient exchange averages them like any other parameter gradient).
+ *   ge_bn_sync_bwd_apply  : dx (+ dres) from the averaged seg_sums. */
+int ge_bn_sync_stats(const void* x, const float* shift, float* sums, void* workspace, size_t workspace_bytes,
+                     int dtype, long long P, long long P_split, int C, ge_stream_t stream);
+int ge_bn_sync_fwd_apply(const void* x, const void* residual, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, long long* num_batches_tracked,
+                         float momentum, float eps, void* out, float* save_mean, float* save_rstd,
+                         void* relu_mask, const float* sums_avg, int world,
+                         int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream);
+int ge_bn_sync_bwd_reduce(const void* dy, const void* relu_mask, const void* x, const float* mean,
+                          const float* rstd, float* seg_sums, float* dgamma, float* dbeta,
+                          void* workspace, size_t workspace_bytes,
+                          int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream);
+int ge_bn_sync_bwd_apply(const void* dy, const void* relu_mask, const void* x, const float* gamma,
+                         const float* mean, const float* rstd, const float* seg_sums_avg, void* dx, void* dres,
+                         int dtype, long long P, long long P_split, int C, int relu, ge_stream_t stream);
+
 /* ---- update_seed: spectral bipartition ------------------------------------------------------
  * What GModule.update_seed asks sklearn's SpectralClustering(2, affinity='nearest_neighbors',
  * n_neighbors, assign_labels='kmeans') for (models/graph_matching.py:532-567), on the device:
