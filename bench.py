@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--clips", type=int, default=None, help="clips per GPU (half source, half target); default per config")
     ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--sync-bn", action="store_true",
-                    help="SyncBatchNorm on the network when N>1 (the reference's intent): fused BatchNorm kernels with the two per-layer NCCL averages, inside the CUDA graphs")
+                    help="SyncBatchNorm on the network when N>1 (the reference's intent): fused BatchNorm kernels with the two per-layer NCCL averages; eager, no CUDA graphs)")
     ap.add_argument("--no-graphs", action="store_true", help="run the static segments eagerly instead of as CUDA graphs")
     ap.add_argument("--fp32", action="store_true", help="fp32 convolutions instead of bf16 autocast")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -396,7 +396,7 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
     w = a.work
-    graphs = not a.no_graphs
+    graphs = not a.no_graphs and not (a.sync_bn and world > 1)
     over = dict(bf16=not a.fp32, sync_bn=a.sync_bn, cluster_backend="device", cuda_graphs=graphs)
     if a.config == 4:
         over["clip_frames"] = w["frames"]

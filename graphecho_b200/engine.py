@@ -301,9 +301,9 @@ class UDAEngine:
         self.network = FPN([2, 4, 23, 3], num_classes=nc, in_channel=1, back_bone=cfg.backbone).to(device)
         self.network = self.network.to(memory_format=torch.channels_last)
         if world_size > 1 and cfg.sync_bn:
-            # the per-layer statistics exchanges run inside the trunk's CUDA graphs on the compute stream while the
-            # gradient buckets travel on the communication stream: they need their own communicator (one NCCL
-            # communicator must not be used from two streams at once)
+            # the per-layer statistics exchanges run on the compute stream while the gradient buckets travel on the
+            # communication stream: they need their own communicator (one NCCL communicator must not be used from two
+            # streams at once)
             import torch.distributed as dist
             self.bn_group = dist.new_group(backend="nccl") if dist.get_backend() == "nccl" else None
             self.network = nn.SyncBatchNorm.convert_sync_batchnorm(self.network, process_group=self.bn_group)
@@ -368,6 +368,10 @@ class UDAEngine:
         change).  Buffers (BatchNorm running statistics, seed banks) are snapshotted before the warm-up / capture
         executions on dummy inputs and restored afterwards: capturing leaves no trace in the model state."""
         cfg, dev = self.cfg, self.device
+        if self.world > 1 and cfg.sync_bn:
+            # measured: capturing the per-layer NCCL averages with make_graphed_callables hangs at replay on 2 ranks
+            # (tests/test_sync_bn_gpu.py history); SyncBatchNorm runs the fused kernels eagerly
+            raise RuntimeError("cuda_graphs with SyncBatchNorm is not supported: use sync_bn=False or cuda_graphs=False")
         ns = n_frames // 2 if n_source is None else int(n_source)
         bufs = self._buffers()
         snapshot = [b.detach().clone() for b in bufs]

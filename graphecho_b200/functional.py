@@ -687,7 +687,7 @@ class _SyncBnAct(Function):
     """Training-mode SyncBatchNorm (+ residual) (+ ReLU) on an NHWC map: the fused BatchNorm kernels with the two small
     cross-rank exchanges (per-segment sums, averaged over the process group) between their statistics and apply stages.
     What nn.SyncBatchNorm does under DDP (the reference's intent, train_cardiac_uda.py:142), per domain segment; the
-    all-reduces are NCCL collectives on the current stream, so the whole layer can be captured in a CUDA graph."""
+    all-reduces are NCCL collectives on the current stream (run eagerly: engine.capture_graphs refuses sync_bn)."""
 
     @staticmethod
     def forward(ctx, x, residual, gamma, beta, running_mean, running_var, nbt, momentum, eps, relu, split, group, world):

