@@ -121,6 +121,98 @@ affinity_pairwise_fwd_kernel(const float* __restrict__ A, const float* __restric
     }
 }
 
+// Forward for batches that fill the machine anyway: 64x64 outputs per CTA, no split-K (each of the 8 warps owns a
+// 32x16 sub-tile, lanes 8x2 register tiles), the hidden axis in passes of 128 channels (same 67 KB of shared memory, 3
+// CTAs/SM).  Per (i,j,k) term the tile staging moves half the bytes of the 32x32 kernel (the L2 -> shared-memory stream
+// was 4.3 GB at 512 problems) and the cross-warp reduction is gone.
+constexpr int BI = 64, BJ = 64, BKC = 128;
+
+__global__ void __launch_bounds__(FWD_THREADS, 3)
+affinity_pairwise_fwd64_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                               const float* __restrict__ w2, const float* __restrict__ b2,
+                               float* __restrict__ M, int N1, int N2, int H) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int ld = BKC + 4;
+    float* nAs = smem;                // [BI][ld]   -a
+    float* Bs = nAs + BI * ld;        // [BJ][ld]
+    float* ws = Bs + BJ * ld;         // [BKC]
+    float* rcs = ws + BKC;            // [BI]
+
+    const int b = blockIdx.z;
+    A += (size_t)b * N1 * H;
+    B += (size_t)b * N2 * H;
+    M += (size_t)b * N1 * N2;
+    const int i0 = blockIdx.y * BI, j0 = blockIdx.x * BJ;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wr = warp >> 2, wc = warp & 3;            // 2 x 4 warps
+    const int li = lane >> 3, lj = lane & 7;
+    const int rbase = wr * 32 + li, cbase = wc * 16 + lj;
+
+    float acc[8][2];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+    float rowc[8];                                      // rows warp + 8 rr
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) rowc[rr] = 0.f;
+
+    for (int k0 = 0; k0 < H; k0 += BKC) {
+        const int kc = min(BKC, H - k0);                // multiple of 32
+        const int h4 = kc >> 2;
+        if (k0 > 0) __syncthreads();
+        for (int e = tid; e < BI * h4; e += FWD_THREADS) {
+            const int r = e / h4, k4 = e - r * h4;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+            if (i0 + r < N1) va = __ldg(reinterpret_cast<const float4*>(A + (size_t)(i0 + r) * H + k0) + k4);
+            if (j0 + r < N2) vb = __ldg(reinterpret_cast<const float4*>(B + (size_t)(j0 + r) * H + k0) + k4);
+            *reinterpret_cast<float4*>(nAs + r * ld + 4 * k4) = make_float4(-va.x, -va.y, -va.z, -va.w);
+            *reinterpret_cast<float4*>(Bs + r * ld + 4 * k4) = vb;
+        }
+        for (int k = tid; k < kc; k += FWD_THREADS) ws[k] = __ldg(w2 + k0 + k);
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const float* ar = nAs + (warp + 8 * rr) * ld;
+            float sdot = 0.f;
+            for (int k = lane; k < kc; k += 32) sdot = fmaf(ws[k], ar[k], sdot);
+            rowc[rr] -= ge::warp_sum(sdot);
+        }
+        for (int k = 0; k < kc; k += 4) {
+            float4 a4[8], b4[2];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) a4[r] = *reinterpret_cast<const float4*>(nAs + (rbase + 4 * r) * ld + k);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) b4[c] = *reinterpret_cast<const float4*>(Bs + (cbase + 8 * c) * ld + k);
+            const float4 w4 = *reinterpret_cast<const float4*>(ws + k);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    acc[r][c] = fmaf(fmaxf(b4[c].x, a4[r].x), w4.x, acc[r][c]);
+                    acc[r][c] = fmaf(fmaxf(b4[c].y, a4[r].y), w4.y, acc[r][c]);
+                    acc[r][c] = fmaf(fmaxf(b4[c].z, a4[r].z), w4.z, acc[r][c]);
+                    acc[r][c] = fmaf(fmaxf(b4[c].w, a4[r].w), w4.w, acc[r][c]);
+                }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) rcs[warp + 8 * rr] = rowc[rr];
+    }
+    __syncthreads();
+    const float bias = __ldg(b2);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = rbase + 4 * r;
+        if (i0 + i >= N1) continue;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int j = cbase + 8 * c;
+            if (j0 + j < N2) M[(size_t)(i0 + i) * N2 + j0 + j] = acc[r][c] + rcs[i] + bias;
+        }
+    }
+}
+
 // Backward sweep: one thread per hidden channel k, a tile of RT rows of P per CTA, a range of rows of Q.
 //   TRANS=false: P=A (rows i), Q=B, g(r,q) = dM[(i0+r)*N2 + q]
 //   TRANS=true : P=B (rows j), Q=A, g(r,q) = dM[q*N2 + (j0+r)]
@@ -361,6 +453,18 @@ extern "C" int ge_affinity_pairwise_fwd(const float* A, const float* B, const fl
     const size_t bytes = smem > red ? smem : red;
     static size_t cached = 0;
     if (int rc = set_smem(affinity_pairwise_fwd_kernel, bytes, cached, "ge_affinity_pairwise_fwd(attr)")) return rc;
+    // 64x64 tiles once they alone fill every SM three times over (3 CTAs/SM); the split-K 32x32 kernel otherwise (a single
+    // 250x250 problem: 64 CTAs x 8 warps instead of 16 CTAs)
+    const long long big_ctas = (long long)batch * ge::cdiv(N1, BI) * ge::cdiv(N2, BJ);
+    if (big_ctas >= 3LL * ge::sm_count()) {
+        const size_t bytes64 = ((size_t)(BI + BJ) * (BKC + 4) + BKC + BI) * sizeof(float);
+        static size_t cached64 = 0;
+        if (int rc = set_smem(affinity_pairwise_fwd64_kernel, bytes64, cached64, "ge_affinity_pairwise_fwd(attr)")) return rc;
+        dim3 grid64(ge::cdiv(N2, BJ), ge::cdiv(N1, BI), batch);
+        affinity_pairwise_fwd64_kernel<<<grid64, FWD_THREADS, bytes64, (cudaStream_t)stream>>>(A, B, w2, b2, M, N1, N2, H);
+        GE_CHECK_LAUNCH("ge_affinity_pairwise_fwd");
+        return GE_OK;
+    }
     dim3 grid(ge::cdiv(N2, TJ), ge::cdiv(N1, TI), batch);
     affinity_pairwise_fwd_kernel<<<grid, FWD_THREADS, bytes, (cudaStream_t)stream>>>(A, B, w2, b2, M, N1, N2, H);
     GE_CHECK_LAUNCH("ge_affinity_pairwise_fwd");

@@ -64,7 +64,8 @@ def test_affinity_pairwise_batched(dev):
     close(M, ref, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("batch,n1,n2,H", [(128, 70, 90, 64), (3, 70, 90, 96), (1, 252, 250, 512), (40, 33, 64, 288)])
+@pytest.mark.parametrize("batch,n1,n2,H", [(128, 70, 90, 64), (3, 70, 90, 96), (1, 252, 250, 512), (40, 33, 64, 288),
+                                          (64, 130, 150, 512)])
 def test_affinity_pairwise_backward_both_modes(dev, batch, n1, n2, H):
     """dA, dB, dw2, db2 against autograd through the literal relu-coupled sum: the split-Q partial mode (small
     batches: one fused sweep for both sides) and the direct mode (one sweep per side once the row tiles fill the
