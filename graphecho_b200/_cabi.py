@@ -34,6 +34,10 @@ _SIGNATURES = {
     "ge_sinkhorn_rpm_bwd": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, P]),
     "ge_matching_loss_fwd": (c_int, [P, P, P, P, P, P, I, I, F, F, P]),
     "ge_matching_loss_bwd": (c_int, [P, P, P, P, P, P, P, I, I, F, F, P]),
+    "ge_stem_conv_supported": (c_int, [I, I]),
+    "ge_stem_conv_fwd": (c_int, [P, P, P, I, I, I, I, P]),
+    "ge_stem_conv_wgrad_workspace_bytes": (c_size_t, [I, I, I]),
+    "ge_stem_conv_wgrad": (c_int, [P, P, P, P, Z, I, I, I, I, P]),
     "ge_sinkhorn_distance_fwd": (c_int, [P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, c_double, P]),
     "ge_sinkhorn_distance_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "ge_knn_graph_set_path": (c_int, [I]),

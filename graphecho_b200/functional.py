@@ -805,6 +805,61 @@ def bn_act(x, bn, residual=None, relu=True):
     return out
 
 
+# ------------------------------------------------------------------------------------------ stem convolution
+class _StemConv(Function):
+    @staticmethod
+    def forward(ctx, x, weight, out_dtype):
+        _need_cuda(x, weight)
+        xf = _f32c(x)
+        wf = _f32c(weight)
+        F_, _, H, W = xf.shape
+        y = torch.empty((F_, 64, H // 2, W // 2), device=x.device, dtype=out_dtype, memory_format=torch.channels_last)
+        dt = BF16 if out_dtype == torch.bfloat16 else F32
+        call("ge_stem_conv_fwd", ptr(xf), ptr(wf), ptr(y), F_, H, W, dt, stream(),
+             work=(4 * F_ * H * W + y.numel() * y.element_size(), 2 * 49 * y.numel()))
+        ctx.save_for_backward(xf)
+        ctx.cfg = (dt, weight.dtype, tuple(weight.shape))
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (xf,) = ctx.saved_tensors
+        dt, wdt, wshape = ctx.cfg
+        F_, _, H, W = xf.shape
+        d = _nhwc_view(dy.to(torch.bfloat16 if dt == BF16 else torch.float32))
+        dw = torch.empty(wshape, device=xf.device, dtype=torch.float32)
+        nbytes = _cabi.lib().ge_stem_conv_wgrad_workspace_bytes(F_, H, W)
+        ws = torch.empty(nbytes, device=xf.device, dtype=torch.uint8)
+        call("ge_stem_conv_wgrad", ptr(xf), ptr(d), ptr(dw), ptr(ws), c_size_t(nbytes), F_, H, W, dt, stream(),
+             work=(4 * F_ * H * W + d.numel() * d.element_size(), 2 * 49 * d.numel()))
+        return None, dw.to(wdt), None
+
+
+USE_STEM_CONV = True
+
+
+def stem_conv(x, conv):
+    """ResNet.conv1 (Conv2d(1, 64, 7, 2, 3, bias=False), fpnseg.py:229) on the direct kernels where they apply (one input
+    channel, data that needs no gradient, even height, width % 8 == 0); the module itself otherwise."""
+    ok = (USE_STEM_CONV and x.is_cuda and x.dim() == 4 and x.shape[1] == 1 and not x.requires_grad and conv.bias is None
+          and tuple(conv.weight.shape) == (64, 1, 7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3)
+          and conv.dilation == (1, 1) and conv.groups == 1
+          and bool(_cabi.lib().ge_stem_conv_supported(int(x.shape[2]), int(x.shape[3]))))
+    if not ok:
+        return conv(x)
+    if torch.is_autocast_enabled():
+        adt = torch.get_autocast_dtype('cuda')
+        if adt != torch.bfloat16:
+            return conv(x)
+        out_dtype = torch.bfloat16
+    else:
+        if x.dtype != torch.float32 or conv.weight.dtype != torch.float32:
+            return conv(x)
+        out_dtype = torch.float32
+    return _StemConv.apply(x, conv.weight, out_dtype)
+
+
 # ------------------------------------------------------------------------------------------ f3: 1x1 conv GEMM + BN statistics
 def conv1x1_tc_supported(P, K, N):
     return bool(_cabi.lib().ge_conv1x1_tc_supported(c_longlong(int(P)), int(K), int(N)))
@@ -1107,7 +1162,8 @@ class _SamplerGather(Function):
         C, dt, shapes, dtypes, dev, per_domain = ctx.meta
         dn = [_f32c(g) if g is not None else None for g in grads[0::2]]
         need = ctx.needs_input_grad[1:]
-        dfeat = [torch.zeros(sh, device=dev, dtype=d_).contiguous(memory_format=torch.channels_last) if nd else None
+        # allocated channels_last from the start (zeros(...).contiguous(channels_last) is a 100 MB strided copy per level)
+        dfeat = [torch.empty(sh, device=dev, dtype=d_, memory_format=torch.channels_last).zero_() if nd else None
                  for sh, d_, nd in zip(shapes, dtypes, need)]
         ent, k = [], 0
         for d, nlev in enumerate(per_domain):

@@ -131,7 +131,7 @@ class ResNet(nn.Module):
 
     def forward_lower(self, x):
         """stem + layer1-3 -> [c1, c2, c3, c4]"""
-        x = GF.bn_act(self.conv1(x), self.bn1, relu=True)
+        x = GF.bn_act(GF.stem_conv(x, self.conv1), self.bn1, relu=True)
         x = GF.maxpool3s2(x) if x.shape[1] % 8 == 0 else self.maxpool(x)
         feats = [x]
         for stage in (self.layer1, self.layer2, self.layer3):

@@ -88,6 +88,18 @@ int ge_matching_loss_fwd(const float* P, const float* lab1, const float* lab2, f
 int ge_matching_loss_bwd(const float* P, const float* lab1, const float* lab2, const int* idx, const float* stats,
                          const float* gout, float* dP, int N1, int N2, float alpha, float gamma, ge_stream_t stream);
 
+/* ---- stem convolution --------------------------------------------------------------------
+ * ResNet.conv1 = Conv2d(1, 64, 7, stride 2, padding 3, bias=False) on gray frames (models/fpnseg.py:229, 251), forward and
+ * weight gradient as direct FP32-pipe kernels (cuDNN has no tensor-core path for one input channel: 0.46 + 0.64 ms of
+ * conversions and sm80 kernels per step).  x fp32 [F,1,H,W]; w / dw fp32 [64,1,7,7]; y / dy [F,H/2,W/2,64] NHWC in `dtype`
+ * (bf16: operands rounded to bf16, fp32 accumulation, as the library's bf16 convolution).  H even, W % 8 == 0, W <= 512.
+ * The input receives no gradient (it is the data). */
+int ge_stem_conv_supported(int H, int W);
+int ge_stem_conv_fwd(const float* x, const float* w, void* y, int F, int H, int W, int dtype, ge_stream_t stream);
+size_t ge_stem_conv_wgrad_workspace_bytes(int F, int H, int W);
+int ge_stem_conv_wgrad(const float* x, const void* dy, float* dw, void* workspace, size_t workspace_bytes,
+                       int F, int H, int W, int dtype, ge_stream_t stream);
+
 /* ---- K5: SinkhornDistance ----------------------------------------------------------------
  * utils/sinkhorn_distance.py:27-86: C_ij = sum_d (x_id-y_jd)^2, <= max_iter log-domain updates
  * with the batch-mean early stop `err < thresh`, pi = exp((-C+u+v)/eps), cost_b = sum pi*C.

@@ -83,3 +83,59 @@ def test_attention_forward_pair_equals_two_calls():
         r2, f2 = m(kv_b, kv_b, q_b)
         for x, y in ((o1, r1), (e1, f1), (o2, r2), (e2, f2)):
             assert x.shape == y.shape and torch.allclose(x, y, rtol=1e-5, atol=1e-6)
+
+
+def _linspace_pick_index(r, m, n_neg_all):
+    """Python port of csrc/sampler.cu::linspace_pick_index (same fp64 operations)."""
+    import math
+    if m <= 0:
+        return -1
+    if m == 1:
+        return 0 if r == 0 else -1
+    stop = float(n_neg_all - 2)
+    step = stop / float(m - 1)
+    i = int(math.floor(float(r) / step)) if step > 0.0 else 0
+    for c in (i - 1, i, i + 1):
+        if c < 0 or c >= m:
+            continue
+        y = stop if c == m - 1 else float(c) * step
+        if int(math.floor(y)) == r:
+            return c
+    return -1
+
+
+def test_sampler_negative_pick_membership_inverts_numpy_linspace():
+    """The sampler kernel decides, per negative location of rank r, whether r is one of
+    floor(linspace(0, n_neg - 2, m)) and which one (graph_matching.py:1001) in closed form.  Exhaustive check of that
+    inversion against numpy over the (n_neg, m) range the sampler can produce (m = num_pos // 8 <= n_neg // 8)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    cases = [(n, m) for n in (2, 3, 9, 10, 17, 64, 100, 101, 777, 1000, 4097) for m in (0, 1, 2, 3, 7, 12, 100, 125, 512)
+             if m <= max(n // 8, 1)]
+    cases += [(int(n), int(rng.integers(1, max(n // 8, 1) + 1))) for n in rng.integers(16, 120000, size=40)]
+    for n_neg, m in cases:
+        picks = np.floor(np.linspace(0, n_neg - 2, m)).astype(np.int64) if m > 0 else np.zeros(0, dtype=np.int64)
+        want = {int(p): i for i, p in enumerate(picks)}
+        assert len(want) == len(picks), (n_neg, m)                  # strictly increasing: no rank is picked twice
+        ranks = range(n_neg) if n_neg <= 5000 else list(picks) + [int(p) + 1 for p in picks] + list(rng.integers(0, n_neg, 200))
+        for r in ranks:
+            assert _linspace_pick_index(int(r), m, n_neg) == want.get(int(r), -1), (n_neg, m, r)
+
+
+def test_sampler_gather_plan_matches_the_reference_counts():
+    """functional.sampler_gather_plan (host half of graph_matching.py:984-1003): strides, pick counts and slot bases."""
+    from graphecho_b200 import functional as GF
+    counts = [(12345, 188000), (150, 40), (99, 5000), (0, 64), (450, 450)]
+    rows, n = GF.sampler_gather_plan(counts)
+    exp = []
+    for n_pos, n_neg in counts:
+        step = n_pos // 100
+        num_pos = len(range(0, n_pos, step)) if step > 1 else n_pos
+        num_neg = n_neg if n_pos > n_neg else num_pos // 8
+        exp.append((num_pos, num_neg))
+    assert [(r[2], r[3]) for r in rows] == exp
+    total_neg = sum(e[1] for e in exp)
+    assert n == total_neg + sum(e[0] for e in exp)
+    assert [r[6] for r in rows] == [sum(e[1] for e in exp[:i]) for i in range(len(exp))]
+    assert [r[5] for r in rows] == [total_neg + sum(e[0] for e in exp[:i]) for i in range(len(exp))]
+    assert [r[4] for r in rows] == [0, 1, 0, 0, 0]

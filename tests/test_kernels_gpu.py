@@ -920,3 +920,35 @@ def test_matching_loss_kernel_vs_oracle(dev, n1, n2, nc):
     (got * 1.0).backward()
     close(got, ref, rtol=2e-5, atol=1e-7)
     close(Pd.grad, Po.grad, rtol=1e-4, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------- stem convolution
+@pytest.mark.parametrize("F_,H,W", [(6, 112, 112), (2, 256, 256), (3, 100, 120), (1, 8, 8)])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_stem_conv_kernels_vs_conv2d(dev, F_, H, W, bf16):
+    """ge_stem_conv_fwd / ge_stem_conv_wgrad against torch's Conv2d(1, 64, 7, 2, 3, bias=False) (fpnseg.py:229): fp32
+    mode against the fp32 convolution; bf16 mode (autocast) against the fp32 convolution of the bf16-rounded operands
+    (what a bf16 convolution with fp32 accumulation computes), output and weight gradient."""
+    torch.manual_seed(H + W)
+    conv = torch.nn.Conv2d(1, 64, 7, 2, 3, bias=False).to(dev)
+    x = torch.randn(F_, 1, H, W, device=dev)
+    g = torch.randn(F_, 64, H // 2, W // 2, device=dev)
+    if bf16:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = GF.stem_conv(x, conv)
+        assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+        gq = g.bfloat16()
+        (dw,) = torch.autograd.grad(y, conv.weight, gq)
+        wq = conv.weight.detach().bfloat16().float().requires_grad_()
+        ref = F.conv2d(x.bfloat16().float(), wq, None, 2, 3)
+        (dref,) = torch.autograd.grad(ref, wq, gq.float())
+        close(y.float(), ref, rtol=1e-2, atol=1e-2)
+        close(dw, dref, rtol=2e-3, atol=2e-3 * float(dref.abs().max()))
+    else:
+        y = GF.stem_conv(x, conv)
+        assert y.dtype == torch.float32 and y.shape == (F_, 64, H // 2, W // 2)
+        (dw,) = torch.autograd.grad(y, conv.weight, g)
+        ref = conv(x)
+        (dref,) = torch.autograd.grad(ref, conv.weight, g)
+        close(y, ref, rtol=1e-4, atol=1e-5)
+        close(dw, dref, rtol=1e-4, atol=1e-4 * float(dref.abs().max()))
