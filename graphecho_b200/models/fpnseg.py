@@ -207,10 +207,10 @@ class FPN(nn.Module):
     def forward_trunk_upper(self, c2, c3, c4):
         """Second part: last backbone stage + lateral / top-down pyramid -> (p2, p3, p4, p5)."""
         c5 = self.back_bone.forward_upper(c4)
-        p5 = self.toplayer(c5)
-        p4 = GF.upsample_add(p5, self.latlayer1(c4))
-        p3 = GF.upsample_add(p4, self.latlayer2(c3))
-        p2 = GF.upsample_add(p3, self.latlayer3(c2))
+        p5 = GF.conv_bias(c5, self.toplayer)
+        p4 = GF.upsample_add(p5, GF.conv_bias(c4, self.latlayer1))
+        p3 = GF.upsample_add(p4, GF.conv_bias(c3, self.latlayer2))
+        p2 = GF.upsample_add(p3, GF.conv_bias(c2, self.latlayer3))
         return p2, p3, p4, p5
 
     def upper_trunk_parameters(self):
@@ -229,15 +229,15 @@ class FPN(nn.Module):
         _need_cuda(x)
         x = x.contiguous(memory_format=torch.channels_last)
         _, c2, c3, c4, c5 = self.back_bone(x)
-        p5 = self.toplayer(c5)
-        p4 = GF.upsample_add(p5, self.latlayer1(c4))
-        p3 = GF.upsample_add(p4, self.latlayer2(c3))
-        p2 = GF.upsample_add(p3, self.latlayer3(c2))
+        p5 = GF.conv_bias(c5, self.toplayer)
+        p4 = GF.upsample_add(p5, GF.conv_bias(c4, self.latlayer1))
+        p3 = GF.upsample_add(p4, GF.conv_bias(c3, self.latlayer2))
+        p2 = GF.upsample_add(p3, GF.conv_bias(c2, self.latlayer3))
         return p2, p3, p4, p5
 
     def forward_head(self, p2, p3, p4, p5):
         """Smoothing + semantic head (fpnseg.py:424-444): pyramid -> logits."""
-        q4, q3, q2 = self.smooth1(p4), self.smooth2(p3), self.smooth3(p2)
+        q4, q3, q2 = GF.conv_bias(p4, self.smooth1), GF.conv_bias(p3, self.smooth2), GF.conv_bias(p2, self.smooth3)
         hw = q2.shape[-2:]
         g1, g2 = self.gn1, self.gn2
 

@@ -952,3 +952,24 @@ def test_stem_conv_kernels_vs_conv2d(dev, F_, H, W, bf16):
         (dref,) = torch.autograd.grad(ref, conv.weight, g)
         close(y, ref, rtol=1e-4, atol=1e-5)
         close(dw, dref, rtol=1e-4, atol=1e-4 * float(dref.abs().max()))
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("k,pad", [(1, 0), (3, 1)])
+def test_conv_bias_fused_add_and_gradient(dev, dtype, k, pad):
+    """GF.conv_bias (library convolution + fused in-place NHWC bias add, streaming bias gradient) against nn.Conv2d:
+    output and the gradients of input, weight and bias (FPN lateral / smoothing convolutions, fpnseg.py:333-345)."""
+    torch.manual_seed(k)
+    conv = torch.nn.Conv2d(64, 256, k, 1, pad).to(dev)
+    x = torch.randn(6, 64, 14, 10, device=dev).contiguous(memory_format=torch.channels_last)
+    g = torch.randn(6, 256, 14, 10, device=dev)
+    xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        ya = GF.conv_bias(xa, conv)
+        ga = torch.autograd.grad(ya, (xa, conv.weight, conv.bias), g.to(ya.dtype))
+        yb = conv(xb)
+        gb = torch.autograd.grad(yb, (xb, conv.weight, conv.bias), g.to(yb.dtype))
+    assert ya.dtype == yb.dtype == dtype
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    close(ya.float(), yb.float(), **tol)
+    for a, b in zip(ga, gb):
+        close(a.float(), b.float(), rtol=tol["rtol"], atol=tol["atol"] * max(1.0, float(b.abs().max())))
