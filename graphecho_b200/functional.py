@@ -1017,6 +1017,25 @@ def conv1x1_bn_act(x, conv, bn, residual=None, relu=True, drop_bias=False):
                                bn.num_batches_tracked, float(bn.momentum), float(bn.eps), bool(relu), int(split))
 
 
+def conv_bn_act(x, conv, bn, residual=None, relu=True):
+    """relu(bn(conv(x)) + residual) for a biased convolution in front of a train-mode nn.BatchNorm2d WITHOUT the bias
+    passes: a per-channel constant in front of train-mode BatchNorm cancels in the output and has a zero gradient; it
+    only shifts the batch mean, so the running mean gets its share added back (state_dict parity with the reference:
+    VGG16's conv + BN + ReLU triples, fpnseg.py:18-166).  ATen would add the bias with a non-vectorised broadcast
+    kernel and reduce its gradient at ~1 TB/s over the largest maps of the network.  Anything else (eval mode, other
+    norm types, no running statistics): the plain composition."""
+    drop = (conv.bias is not None and bn.training and type(bn) is torch.nn.BatchNorm2d and bn.affine
+            and bn.track_running_stats and bn.momentum is not None and x.is_cuda)
+    if not drop:
+        return bn_act(conv(x), bn, residual=residual, relu=relu)
+    y = conv1x1_bn_act(x, conv, bn, residual=residual, relu=relu, drop_bias=True)
+    with torch.no_grad():
+        # one running-mean update per BatchNorm segment (domain_split): 1 - (1-m)^nseg of the bias in total
+        share = 1.0 - (1.0 - float(bn.momentum)) ** bn_segments(x.shape[0])
+        bn.running_mean.add_(conv.bias.detach().to(bn.running_mean.dtype), alpha=share)
+    return y
+
+
 USE_CONV1X1_TC = True       # measured >= cuDNN + statistics kernel at every eligible shape (profiles/r2_conv1x1_tc.md)
 
 

@@ -51,7 +51,7 @@ class VGG16(nn.Module):
         for b in range(first, last + 1):
             mods = list(getattr(self, f"block_{b}"))
             for i in range(0, len(mods) - 1, 3):          # (conv, BN, ReLU) triples -> conv + fused BN+ReLU
-                x = GF.bn_act(mods[i](x), mods[i + 1], relu=True)
+                x = GF.conv_bn_act(x, mods[i], mods[i + 1], relu=True)    # the conv bias cancels in train-mode BN
             x = mods[-1](x)                                # max-pool
             feats.append(x)
         return feats
