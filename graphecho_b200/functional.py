@@ -990,7 +990,8 @@ class _Conv1x1BnAct(Function):
              work=(P * Cout * 2 * (3 + (1 if has_res else 0)) + (P * Cout // 8 if relu else 0), 16 * P * Cout))
         dy2 = dy.permute(0, 2, 3, 1).reshape(P, Cout)
         dx2 = dy2 @ w2                                            # dgrad  [P,Cout] x [Cout,K]
-        dw = (dy2.t() @ x2).float().reshape(wshape).to(wdt)       # wgrad  [Cout,P] x [P,K]
+        dw = dy2.t() @ x2                                         # wgrad  [Cout,P] x [P,K]  (bf16 product)
+        dw = (dw if wdt == torch.bfloat16 else dw.float()).reshape(wshape).to(wdt)
         Nb, _, H, W = xshape
         dx = dx2.view(Nb, H, W, K).permute(0, 3, 1, 2)
         return dx, dw, dres, dgb[0].to(gdt), dgb[1].to(bdt), None, None, None, None, None, None, None
