@@ -139,3 +139,62 @@ def test_sampler_gather_plan_matches_the_reference_counts():
     assert [r[6] for r in rows] == [sum(e[1] for e in exp[:i]) for i in range(len(exp))]
     assert [r[5] for r in rows] == [total_neg + sum(e[0] for e in exp[:i]) for i in range(len(exp))]
     assert [r[4] for r in rows] == [0, 1, 0, 0, 0]
+
+
+def test_sinkhorn_exponent_domain_restatement_equals_the_log_domain_reference():
+    """The algebra csrc/sinkhorn_rpm_reg.cu relies on, in fp64 on the CPU: with K = exp(z), u = exp(-r), v = exp(-c) the
+    slack-padded log-domain iteration (graph_matching.py:637-676) is u <- 1/(1 + K v), v <- 1/(1 + K^T u), P = K u v^T;
+    and the exact adjoint of the unrolled loop is dz = K o F with F accumulated as rank-1 updates
+    (x = gc v_t, gr -= u_t (K x), y = gr u_t, F += u_t x^T + y v_{t-1}^T, gc = -v_{t-1} (K^T y)).  Checked against
+    autograd through the oracle's literal log-domain loop."""
+    import torch
+    from oracle import graph_ops as G
+    torch.manual_seed(0)
+    for n1, n2, T in ((7, 5, 20), (12, 17, 6), (3, 3, 1)):
+        z = (torch.randn(n1, n2, dtype=torch.float64) * 1.3).requires_grad_()
+        W = torch.randn(n1, n2, dtype=torch.float64)
+        P_ref = G.sinkhorn_rpm(z[None], n_iters=T, slack=True)[0].exp()
+        (P_ref * W).sum().backward()
+        K = z.detach().exp()
+        u, v = torch.ones(n1, dtype=torch.float64), torch.ones(n2, dtype=torch.float64)
+        hu, hv = [], []
+        for _ in range(T):
+            u = 1.0 / (1.0 + K @ v)
+            v = 1.0 / (1.0 + K.t() @ u)
+            hu.append(u)
+            hv.append(v)
+        P = K * u[:, None] * v[None, :]
+        assert torch.allclose(P, P_ref.detach(), rtol=1e-12, atol=1e-14)
+        F = W * hu[-1][:, None] * hv[-1][None, :]
+        E = K * F
+        gr, gc = -E.sum(1), -E.sum(0)
+        for t in range(T - 1, -1, -1):
+            vprev = hv[t - 1] if t > 0 else torch.ones(n2, dtype=torch.float64)
+            x = gc * hv[t]
+            gr = gr - hu[t] * (K @ x)
+            y = gr * hu[t]
+            F = F + hu[t][:, None] * x[None, :] + y[:, None] * vprev[None, :]
+            gc = -vprev * (K.t() @ y)
+            gr = torch.zeros_like(gr)
+        assert torch.allclose(K * F, z.grad, rtol=1e-10, atol=1e-13)
+
+
+def test_affinity_identities_used_by_the_kernels():
+    """csrc/affinity.cu: relu(a + b) == a + max(b, -a) bit for bit in fp32 (forward at 2 issue slots per term), the ReLU
+    gate a + b > 0 <=> b > -a, and dw_k = sum_i a_ik s_ik + sum_j b_jk t_jk with the UNWEIGHTED gated sums s, t."""
+    import torch
+    torch.manual_seed(1)
+    a = torch.cat([torch.randn(4000) * 3, torch.tensor([0.0, -0.0, 1e-30, -1e-30, 3.0, -3.0, 1e20, -1e20])])
+    b = torch.cat([torch.randn(4000) * 3, torch.tensor([0.0, 0.0, -1e-30, 1e-30, -3.0, 3.0, -1e20, 1e20])])
+    lhs, rhs = torch.relu(a + b), a + torch.maximum(b, -a)
+    assert torch.equal(lhs, rhs)
+    assert torch.equal((a + b) > 0, b > -a)
+    A, B = torch.randn(9, 16, dtype=torch.float64), torch.randn(11, 16, dtype=torch.float64)
+    w = torch.randn(16, dtype=torch.float64, requires_grad=True)
+    g = torch.randn(9, 11, dtype=torch.float64)
+    M = (torch.relu(A[:, None, :] + B[None, :, :]) * w).sum(-1)
+    (dw,) = torch.autograd.grad(M, w, g)
+    gate = ((A[:, None, :] + B[None, :, :]) > 0).to(torch.float64)
+    s = (g[:, :, None] * gate).sum(1)            # [N1, H]
+    t = (g[:, :, None] * gate).sum(0)            # [N2, H]
+    assert torch.allclose(dw, (A * s).sum(0) + (B * t).sum(0), rtol=1e-12, atol=1e-12)
